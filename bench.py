@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- GR2M cell-months/s (+ routed cell-months/s) on N B200s, beside the host-CPU oracle.
+
+One "step" = one pass of the calibration hot path over the whole workload: every candidate
+parameter set simulated on every subbasin for every month, outlet series and objective value per set
+(Optim_GR2MSemiDistr's OFUN, R/Optim_GR2MSemiDistr.R:125-217, batched).  Workload = BASELINE.json
+configs[3] "C4": 1e5 subbasins x 1e4 parameter sets x 480 months, synthetic forcing.
+With N GPUs the parameter sets are sharded across ranks (forcing replicated, no data-path
+collective); objective values are all-gathered over NCCL at the end of each step.  Total work is
+fixed, so scaling is "strong".
+
+  value     cell-months/s with forcing and parameters resident in HBM, objective left on the device
+  e2e       same metric through the host-buffer C ABI (gr2m_basin_create + gr2m_objective_batch +
+            destroy): forcing H2D from pinned memory and objective D2H inside the timed region
+  roofline  recursion kernel vs the FP64 pipe (measured DFMA peak)
+  routing   secondary metric: routed cell-months/s of the batched WFA sweep on a synthetic D8 grid
+  cpu_baseline  the CPU oracle (a port: the reference's R/airGR/TauDEM path cannot run here) timed
+            on this box's host cores on a bounded sample of the same workload
+
+`--impl reference` times that CPU path alone (all host threads), same metric/config keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gr2m_cell_months_per_sec"
+UNIT = "cell-months/s"
+FLOP_PER_UNIT_ALGO = 67          # nominal FP64 operations per (cell, set, month)
+FP64_INSTR_PER_UNIT = 104        # FP64-pipe SASS instructions per unit of k_gr2m_calib<true> (profiles/)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=100_000)
+    ap.add_argument("--sets", type=int, default=10_000)
+    ap.add_argument("--months", type=int, default=480)
+    ap.add_argument("--route-n", type=int, default=20_000, help="side of the synthetic D8 grid (0 = skip routing)")
+    ap.add_argument("--route-batch", type=int, default=16, help="months per routing batch")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--literal", action="store_true", help="use the literal (IEEE division) kernel variant")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"C4 calibration sweep: {a.cells} subbasins x {a.sets} parameter sets x {a.months} months"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower() == "active"})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port(a, nthreads, seconds):
+    """Time the CPU oracle's OFUN batch on a bounded sample (same forcing generator, same months)."""
+    import oracle
+    from gr2msemidistr_b200 import synth
+    oracle.build()
+    cells = min(a.cells, 2000)
+    P, E, area, nd = synth.forcing(cells, a.months)
+    region = np.zeros(cells, np.int32)
+    qobs = synth.qobs_from(np.full(a.months, 100.0))
+    # calibrate the sample size on a tiny run, then size it for ~`seconds`
+    par = synth.param_sets(max(nthreads, 8))
+    t0 = time.perf_counter()
+    oracle.objective_batch(P, E, area, nd, region, 1, par, qobs, warmup=36, nthreads=nthreads, want_qt=False)
+    dt = time.perf_counter() - t0
+    rate = cells * a.months * len(par) / dt
+    nsets = int(max(len(par), min(a.sets, rate * seconds / (cells * a.months))))
+    nsets = max(nthreads, (nsets // nthreads) * nthreads)
+    par = synth.param_sets(nsets)
+    t0 = time.perf_counter()
+    oracle.objective_batch(P, E, area, nd, region, 1, par, qobs, warmup=36, nthreads=nthreads, want_qt=False)
+    dt = time.perf_counter() - t0
+    units = cells * a.months * nsets
+    return {"value": units / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"{cells} subbasins x {nsets} sets x {a.months} months of the C4 generator, {dt:.1f} s, "
+                      f"oracle/gr2m_oracle.c (gcc -O2) with {nthreads} pthreads over parameter sets"}, units, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    vals, last = [], None
+    per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    for i in range(a.warmup + a.steps):
+        cb, units, dt = cpu_port(a, nthreads, per_step)
+        if i >= a.warmup:
+            vals.append((units, dt))
+        last = cb
+    units = sum(u for u, _ in vals)
+    dt = sum(d for _, d in vals)
+    v = units / dt
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dt / max(1, a.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "l2": "inputs larger than L2"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference's own R/airGR/TauDEM path cannot run in this image (no R, gfortran, MPI, TauDEM); "
+                    "this is the CPU oracle port, a lower bound on the reference's time"}
+    print(json.dumps(line), flush=True)
+
+
+def bench_routing(a, capi, torch, rank, world, dist):
+    """Secondary metric: batched WFA sweep, months sharded across ranks (plan replicated)."""
+    from gr2msemidistr_b200 import synth
+    n = a.route_n
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t0 = time.perf_counter()
+    d8 = synth.d8_grid(n, n, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    plan = capi.Plan(dev_ptr=d8.data_ptr(), shape=(n, n))
+    t_plan = time.perf_counter() - t0
+    del d8
+    torch.cuda.empty_cache()
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+    ncell, ld = n * n, a.route_batch
+    months_total = a.months
+    my_months = months_total // world + (1 if rank < months_total % world else 0)
+    nb = (my_months + ld - 1) // ld
+    A = torch.empty((ncell, ld), dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def one_pass(timed):
+        tot = 0.0
+        for b in range(nb):
+            A.uniform_(0.0, 100.0, generator=gen)       # synthetic dense weights, made on the device (untimed)
+            m = min(ld, my_months - b * ld)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.accumulate_dev(A.data_ptr(), m, ld)
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+
+    one_pass(False)
+    ms = one_pass(True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    units = float(ncell) * months_total
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    gbs = units / world * 16.0 / (ms * 1e-3) / 1e9
+    out = {"metric": "routed_cell_months_per_sec", "value": units / (ms * 1e-3), "unit": UNIT,
+           "workload": f"C5 WFA: {n} x {n} synthetic D8 grid x {months_total} months, dense FP64 weights, "
+                       f"{ld}-month batches, months sharded over {world} GPU(s)",
+           "ms_per_pass": ms, "levels": plan.nlevels, "cells_in_order": plan.norder,
+           "plan_build_s": t_plan, "grid_gen_s": t_gen,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                        "traffic": None, "algorithmic_bytes_per_unit": 16}}
+    plan.close()
+    del A
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+    from gr2msemidistr_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    capi.lib()
+    capi.set_device(local)
+    torch.cuda.set_device(local)
+
+    # ---- inputs (every rank generates the same seeded arrays; forcing is replicated) ----------
+    P, E, area, nd = synth.forcing(a.cells, a.months)
+    region = np.zeros(a.cells, np.int32)
+    par_all = synth.param_sets(a.sets)
+    qobs = synth.qobs_from(np.full(a.months, 100.0) * (1 + 0.5 * np.sin(np.arange(a.months) / 6.0)))
+    s0 = a.sets * rank // world
+    s1 = a.sets * (rank + 1) // world
+    par = np.ascontiguousarray(par_all[s0:s1])
+    nloc = s1 - s0
+    flags = capi.MATH_LITERAL if a.literal else 0
+
+    stream = torch.cuda.current_stream()
+    basin = capi.Basin(P, E, area, nd, region, 1)
+    basin.set_stream(stream.cuda_stream)
+    par_d = torch.from_numpy(par).to(dev)
+    of_d = torch.empty(nloc, dtype=torch.float64, device=dev)
+    of_all = torch.empty(a.sets, dtype=torch.float64, device=dev) if world > 1 else of_d
+    counts = [a.sets * (r + 1) // world - a.sets * r // world for r in range(world)]
+
+    def step():
+        basin.objective_batch_dev(par_d.data_ptr(), nloc, qobs, 36, capi.OF_KGE, flags, of_d.data_ptr())
+        if world > 1:
+            if len(set(counts)) == 1:
+                dist.all_gather_into_tensor(of_all, of_d)
+            else:
+                dist.all_gather(list(of_all.split(counts)), of_d)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    kern_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+        kern_ms.append(None)
+    e1.record()
+    fence()
+    ms_total = e0.elapsed_time(e1)
+    last_kernel_ms = basin.last_kernel_ms()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total, last_kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms = float(t[0]), float(t[1])
+    units_step = float(a.cells) * a.sets * a.months
+    value = units_step * a.steps / (ms_total * 1e-3)
+    of_host = of_all.cpu().numpy()
+
+    # ---- roofline of the recursion kernel ------------------------------------------------------
+    peak_tf = capi.fp64_peak_tflops(4096)
+    units_kernel = float(a.cells) * nloc * a.months
+    ach_tf = units_kernel * FP64_INSTR_PER_UNIT * 2.0 / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": None,
+                "kernel": "k_gr2m_calib<fast>" if not a.literal else "k_gr2m_calib<literal>",
+                "kernel_ms": kernel_ms, "units_per_launch": units_kernel,
+                "fp64_instr_per_unit": FP64_INSTR_PER_UNIT,
+                "achieved_def": "FP64-pipe instructions issued per unit (SASS count, profiles/) x units x 2 flop "
+                                "(DFMA-slot equivalents) / CUDA-event kernel time",
+                "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak), 2 flop per DFMA",
+                "algorithmic_flop_per_unit": FLOP_PER_UNIT_ALGO,
+                "achieved_algorithmic_tflops": units_kernel * FLOP_PER_UNIT_ALGO / (kernel_ms * 1e-3) / 1e12,
+                "survey_ceiling_units_per_s": 7.4e10,
+                "frac_of_survey_ceiling": units_kernel / (kernel_ms * 1e-3) / 7.4e10}
+
+    # ---- end to end through the host-buffer C ABI ---------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        Pp = torch.from_numpy(P).pin_memory()
+        Ep = torch.from_numpy(E).pin_memory()
+        parp = torch.from_numpy(par).pin_memory()
+        basin.close()
+        n_e2e = max(1, min(a.steps, 2))
+
+        def e2e_step():
+            with capi.Basin(Pp.numpy(), Ep.numpy(), area, nd, region, 1) as b:
+                r = b.objective_batch(parp.numpy(), qobs, 36, capi.OF_KGE, flags, want_crit=False)
+            return r["of"]
+
+        e2e_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            of_e2e = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        same = bool(np.array_equal(of_e2e, of_host[s0:s1], equal_nan=True))
+        e2e = {"value": units_step * n_e2e / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(P.nbytes + E.nbytes + area.nbytes + nd.nbytes + region.nbytes + par.nbytes + qobs.nbytes),
+               "d2h_bytes_per_step": int(nloc * 8), "steps": n_e2e, "matches_resident_run": same,
+               "api": "gr2m_basin_create + gr2m_objective_batch + gr2m_basin_destroy (pinned host buffers)"}
+    else:
+        basin.close()
+
+    routing = None
+    if a.route_n > 0:
+        try:
+            routing = bench_routing(a, capi, torch, rank, world, dist)
+        except Exception as ex:   # report, do not lose the headline line
+            routing = {"error": repr(ex)}
+
+    cpu = None
+    if rank == 0 and not a.no_cpu:
+        cpu, _, _ = cpu_port(a, os.cpu_count() or 1, a.cpu_seconds)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "sets_per_gpu": nloc, "objective": "KGE", "warmup_months": 36,
+                           "l2": "forcing (768 MB) and outlet partials larger than L2; no flush needed",
+                           "parallelism": f"parameter sets sharded over {world} GPU(s), forcing replicated"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": 2 * a.steps, "clocks": clocks, "routing": routing,
+                "objective_checksum": float(np.nansum(of_host))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+// common.cuh -- shared host/device helpers for libgr2m_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gr2m_b200.h"
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void gr2m_set_error(const char *fmt, ...);
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+            return (e_ == cudaErrorMemoryAllocation) ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA;            \
+        }                                                                                          \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                         \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            gr2m_set_error("%s: %s", __func__, msg);                                               \
+            return GR2M_ERR_INVALID;                                                               \
+        }                                                                                          \
+    } while (0)
+
+int gr2m_check_device(void);   // GR2M_OK, or GR2M_ERR_NODEVICE with the error text set
+int gr2m_current_device(void);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- warp helpers -----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double shfl_xor_f64(double v, int m)
+{
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v)   // fixed butterfly order, all lanes get it
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor_f64(v, m);
+    return v;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared, completes `bytes` on the mbarrier; addresses and size multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif  // __CUDACC__

@@ -1,0 +1,753 @@
+// gr2m.cu -- GR2M recursion + objective kernels and their C ABI (sm_100a).
+//
+// Data layout in HBM (owned by gr2m_basin):
+//   F      tiled month-major forcing  F[tile][t][var][lane]  doubles, tile = 32 consecutive cells,
+//          var 0 = P, 1 = E, t < ntime_pad (ntime rounded up to TM months, zero padded).  One stage of
+//          TM months of one tile is ONE contiguous TM*512-byte block, fetched by a single 1-D bulk
+//          async copy (TMA engine, UBLKCP) into shared memory and shared by all sets of the block;
+//          inside a stage the 32 lanes of a warp read 32 consecutive doubles (coalesced, conflict-free).
+//   area, region   per cell;  den[t] = 86.4*nDays[t], conv[t] = 1/den[t]   (Run:229)
+// Thread mapping (north_star): one thread per (cell, parameter set); lanes of a warp = 32 cells of a
+// tile, warps of a block = SPB parameter sets; S and R live in registers for all months.
+#include "gr2m_math.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <new>
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing / device selection
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int g_device = 0;
+
+void gr2m_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *gr2m_last_error(void) { return g_err; }
+extern "C" int gr2m_version(void) { return 1; }
+
+extern "C" int gr2m_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gr2m_check_device(void)
+{
+    if (gr2m_device_count() <= 0) {
+        gr2m_set_error("no CUDA device available (libgr2m_b200 has no CPU path)");
+        return GR2M_ERR_NODEVICE;
+    }
+    return GR2M_OK;
+}
+
+int gr2m_current_device(void) { return g_device; }
+
+extern "C" int gr2m_set_device(int device)
+{
+    int n = gr2m_device_count();
+    if (n <= 0) return gr2m_check_device();
+    REQUIRE(device >= 0 && device < n, "device index out of range");
+    g_device = device;
+    CK(cudaSetDevice(device));
+    return GR2M_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int TM = 16;    // months per shared-memory stage
+constexpr int NST = 3;    // stages in flight
+constexpr int SPB = 8;    // parameter sets (warps) per block
+constexpr int STAGE_DBL = TM * 64;
+
+// raw [ncell][ntime] (R column-major) -> tiled month-major F[tile][t][var][32]
+__global__ void k_tile_forcing(const double *__restrict__ P, const double *__restrict__ E, int ncell, int ntime,
+                               int ntime_pad, double *__restrict__ F)
+{
+    __shared__ double sp[32][33], se[32][33];
+    int tile = blockIdx.x, t0 = blockIdx.y * 32;
+    int lx = threadIdx.x, ly = threadIdx.y;   // 32 x 8
+    for (int j = ly; j < 32; j += 8) {
+        int c = tile * 32 + j, t = t0 + lx;
+        bool ok = c < ncell && t < ntime;
+        sp[j][lx] = ok ? P[(size_t)c * ntime + t] : 0.0;
+        se[j][lx] = ok ? E[(size_t)c * ntime + t] : 0.0;
+    }
+    __syncthreads();
+    for (int j = ly; j < 32; j += 8) {
+        int t = t0 + j;
+        if (t < ntime_pad) {
+            size_t base = ((size_t)tile * ntime_pad + t) * 64;
+            F[base + lx] = sp[lx][j];
+            F[base + 32 + lx] = se[lx][j];
+        }
+    }
+}
+
+// out[c][r] = in[r][c]  (in: rows x cols with leading dimension ldin; out: cols x rows)
+__global__ void k_transpose(const double *__restrict__ in, int rows, int cols, int ldin, double *__restrict__ out)
+{
+    __shared__ double s[32][33];
+    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) s[j][threadIdx.x] = in[(size_t)r * ldin + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = s[threadIdx.x][j];
+    }
+}
+
+__device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int nreg, int reg, double area)
+{
+    CellPar p;
+    p.X1 = fmax(par[reg], 0.01);             // RunModel_GR2M.R floors X1, X2 at 1e-2
+    p.X2 = fmax(par[nreg + reg], 0.01);
+    p.fp = par[2 * nreg + reg];
+    p.fe = par[3 * nreg + reg];
+    p.iX1 = 1.0 / p.X1;
+    p.area = area;
+    return p;
+}
+
+// 8 values per lane -> sums over the 32 lanes; lanes with (lane & 3) == 0 return the total of value
+// index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1).  9 adds + 9 shuffles for 8 reductions,
+// fixed association order (deterministic).
+__device__ __forceinline__ double warp_reduce8(const double (&v)[8], int lane)
+{
+    double w[4], u[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+        w[i] = keep + shfl_xor_f64(send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        double send = hi ? w[i] : w[i + 2], keep = hi ? w[i + 2] : w[i];
+        u[i] = keep + shfl_xor_f64(send, 8);
+    }
+    hi = lane & 4;
+    double send = hi ? u[0] : u[1], keep = hi ? u[1] : u[0];
+    double s = keep + shfl_xor_f64(send, 4);
+    s += shfl_xor_f64(s, 2);
+    s += shfl_xor_f64(s, 1);
+    return s;
+}
+
+struct CalibArgs {
+    const double *F, *area, *params, *tconv;   // tconv: conv[t] (fast) or den[t] (literal)
+    const int *region;
+    double *partial;                           // [csplit][nsets][ntime]
+    int ncell, ntiles, ntime, ntime_pad, nreg, nsets, nsg, tiles_per_split, f32exp;
+};
+
+// Calibration-mode recursion: every (cell, set) is simulated for all months; only the outlet sums
+// sum_c QS[t, c] per (set, month) leave the SM (Optim:186-196).  Block = SPB sets x (a range of cell
+// tiles processed one after another); forcing stages arrive by bulk async copy and are reused by
+// all SPB sets; per-set outlet accumulators live in shared memory across the tile loop.
+template <bool FAST>
+__global__ void __launch_bounds__(SPB * 32, 3) k_gr2m_calib(CalibArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);   // NST * STAGE_DBL
+    double *qacc = stage + NST * STAGE_DBL;                 // SPB * ntime_pad
+    double *tconv = qacc + SPB * a.ntime_pad;               // ntime_pad
+    double *tab = tconv + a.ntime_pad;                      // 32
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 32);   // NST
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
+    const int set = sg * SPB + warp;
+    const bool set_ok = set < a.nsets;
+    const int tile0 = cs * a.tiles_per_split;
+    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
+    const int nchunk = a.ntime_pad / TM;
+    const int total = (tile1 - tile0) * nchunk;
+
+    for (int i = tid; i < SPB * a.ntime_pad; i += blockDim.x) qacc[i] = 0.0;
+    for (int i = tid; i < a.ntime_pad; i += blockDim.x) tconv[i] = i < a.ntime ? a.tconv[i] : 1.0;
+    if (tid < 32) tab[tid] = c_exp2_tab[tid];
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;   // stages of consecutive tiles are contiguous
+    if (tid == 0) {
+        for (int g = 0; g < NST - 1 && g < total; ++g) {
+            mbar_arrive_expect_tx(&full[g], STAGE_DBL * 8);
+            bulk_g2s(stage + g * STAGE_DBL, Fbase + (size_t)g * STAGE_DBL, STAGE_DBL * 8, &full[g]);
+        }
+    }
+
+    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4 * a.nreg;
+    int g = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int cell = tile * 32 + lane;
+        const bool cell_ok = cell < a.ncell;
+        CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0);
+        double S = 0.3 * p.X1, R = 0.5 * p.X2;   // airGR default IniResLevels (Optim never passes IniState)
+        for (int ch = 0; ch < nchunk; ++ch, ++g) {
+            if (tid == 0 && g + NST - 1 < total) {
+                int gn = g + NST - 1, sn = gn % NST;
+                mbar_arrive_expect_tx(&full[sn], STAGE_DBL * 8);
+                bulk_g2s(stage + sn * STAGE_DBL, Fbase + (size_t)gn * STAGE_DBL, STAGE_DBL * 8, &full[sn]);
+            }
+            mbar_wait(&full[g % NST], (g / NST) & 1);
+            if (set_ok) {
+                const double *sp = stage + (g % NST) * STAGE_DBL;
+#pragma unroll
+                for (int h = 0; h < TM / 8; ++h) {
+                    double v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int mm = h * 8 + m, t = ch * TM + mm;
+                        double Pr = sp[mm * 64 + lane], Er = sp[mm * 64 + 32 + lane];
+                        StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab)
+                                         : step_literal(p, Pr, Er, S, R, a.f32exp);
+                        v[m] = FAST ? (p.area * o.Q) * tconv[t] : (p.area * o.Q) / tconv[t];
+                    }
+                    double s = warp_reduce8(v, lane);
+                    if ((lane & 3) == 0) {
+                        int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        qacc[warp * a.ntime_pad + ch * TM + h * 8 + idx] += s;
+                    }
+                }
+            }
+            __syncthreads();   // stage g%NST is free again (refilled by the copy issued next iteration)
+        }
+    }
+    if (set_ok)
+        for (int t = lane; t < a.ntime; t += 32)
+            a.partial[((size_t)cs * a.nsets + set) * a.ntime + t] = qacc[warp * a.ntime_pad + t];
+}
+
+struct SimArgs {
+    const double *F, *area, *params, *den, *S0, *R0;
+    const int *region;
+    double *out;        // [5][ntime][ncell_pad] month-major: PR, AE, SM, RU, QS
+    double *S_end, *R_end;
+    int ncell, ncell_pad, ntime, ntime_pad, nreg, f32exp;
+};
+
+// Simulation-mode recursion: one parameter vector, every series written (Run:223-229).
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_gr2m_sim(SimArgs a)
+{
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.ncell_pad) return;
+    const bool ok = cell < a.ncell;
+    const int tile = cell >> 5, lane = cell & 31;
+    CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0);
+    double S = (a.S0 && ok) ? a.S0[cell] : 0.3 * p.X1;
+    double R = (a.R0 && ok) ? a.R0[cell] : 0.5 * p.X2;
+    const double *f = a.F + (size_t)tile * a.ntime_pad * 64 + lane;
+    const size_t plane = (size_t)a.ntime * a.ncell_pad;
+    for (int t = 0; t < a.ntime; ++t) {
+        double Pr = f[(size_t)t * 64], Er = f[(size_t)t * 64 + 32];
+        StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab) : step_literal(p, Pr, Er, S, R, a.f32exp);
+        size_t k = (size_t)t * a.ncell_pad + cell;
+        a.out[k] = o.Pc;
+        a.out[plane + k] = o.AE;
+        a.out[2 * plane + k] = S;
+        a.out[3 * plane + k] = o.Q;
+        a.out[4 * plane + k] = (p.area * o.Q) / a.den[t];
+    }
+    if (ok) {
+        if (a.S_end) a.S_end[cell] = S;
+        if (a.R_end) a.R_end[cell] = R;
+    }
+}
+
+struct ObjArgs {
+    const double *partial, *qobs;   // partial [csplit][nsets][ntime]
+    double *qt, *of, *crit;         // qt [nsets][ntime] (scratch or output), of [nsets], crit [nsets][3]
+    int csplit, nsets, ntime, warmup, which, single_cell, unrounded, has_obs;
+};
+
+// Objective (Optim:186-216): one warp per parameter set.  sink = round(sum over cell splits, 2);
+// warm-up and NA pairs dropped; hydroGOF KGE("2009") / NSE / rmse with two-pass moments.
+__global__ void __launch_bounds__(128) k_objective(ObjArgs a)
+{
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (set >= a.nsets) return;
+    double *qt = a.qt + (size_t)set * a.ntime;
+    for (int t = lane; t < a.ntime; t += 32) {
+        double s = 0.0;
+        for (int c = 0; c < a.csplit; ++c) s += a.partial[((size_t)c * a.nsets + set) * a.ntime + t];
+        qt[t] = (a.single_cell || a.unrounded) ? s : r_round_dig(s, 2);
+    }
+    __syncwarp();
+    if (!a.has_obs) return;
+    // pass 1: n, means (R's mean(): sum/n then one refinement pass)
+    double n = 0.0, ss = 0.0, so = 0.0;
+    for (int t = a.warmup + lane; t < a.ntime; t += 32) {
+        double s = qt[t], o = a.qobs[t];
+        if (!isnan(s) && !isnan(o)) { n += 1.0; ss += s; so += o; }
+    }
+    n = warp_sum_f64(n); ss = warp_sum_f64(ss); so = warp_sum_f64(so);
+    double ms = ss / n, mo = so / n, cs = 0.0, co = 0.0;
+    for (int t = a.warmup + lane; t < a.ntime; t += 32) {
+        double s = qt[t], o = a.qobs[t];
+        if (!isnan(s) && !isnan(o)) { cs += s - ms; co += o - mo; }
+    }
+    ms += warp_sum_f64(cs) / n;
+    mo += warp_sum_f64(co) / n;
+    // pass 2: centred second moments and squared errors
+    double sse = 0.0, den = 0.0, vs = 0.0, vo = 0.0, cv = 0.0;
+    for (int t = a.warmup + lane; t < a.ntime; t += 32) {
+        double s = qt[t], o = a.qobs[t];
+        if (!isnan(s) && !isnan(o)) {
+            double d = o - s, x = s - ms, y = o - mo;
+            sse += d * d; den += y * y; vs += x * x; vo += y * y; cv += x * y;
+        }
+    }
+    sse = warp_sum_f64(sse); den = warp_sum_f64(den); vs = warp_sum_f64(vs); vo = warp_sum_f64(vo);
+    cv = warp_sum_f64(cv);
+    // rmse = sqrt(mean(d^2)) with R's two-pass mean
+    double mse = sse / n, cm = 0.0;
+    for (int t = a.warmup + lane; t < a.ntime; t += 32) {
+        double s = qt[t], o = a.qobs[t];
+        if (!isnan(s) && !isnan(o)) { double d = s - o; cm += d * d - mse; }
+    }
+    mse += warp_sum_f64(cm) / n;
+    if (lane == 0) {
+        double nse = NAN, kge = NAN, rmse = NAN;
+        if (n > 0.0) {
+            if (den != 0.0) nse = 1.0 - sse / den;
+            rmse = sqrt(mse);
+            if (n > 1.0) {
+                double sd_s = sqrt(vs / (n - 1.0)), sd_o = sqrt(vo / (n - 1.0));
+                double r = cv / (sqrt(vs) * sqrt(vo));
+                r = fmin(fmax(r, -1.0), 1.0);
+                double alpha = sd_s / sd_o, beta = ms / mo;
+                if (mo != 0.0 || sd_o != 0.0) {
+                    double x = r - 1.0, y = alpha - 1.0, z = beta - 1.0;
+                    kge = 1.0 - sqrt(x * x + y * y + z * z);
+                }
+            }
+        }
+        if (a.crit) { a.crit[3 * set] = kge; a.crit[3 * set + 1] = nse; a.crit[3 * set + 2] = rmse; }
+        if (a.of) {
+            double v = a.which == GR2M_OF_KGE ? 1.0 - r_round_dig(kge, 3)
+                     : a.which == GR2M_OF_NSE ? 1.0 - r_round_dig(nse, 3) : r_round_dig(rmse, 3);
+            a.of[set] = v;
+        }
+    }
+}
+
+// test hook: element-wise device math (op 0 r_round1, 1 r_round1_exact, 2 exp_tab, 3 div_fast,
+// 4 rcbrt_fast, 5 r_round_dig(x, (int)y))
+__global__ void k_debug_math(int op, int n, const double *x, const double *y, double *out)
+{
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    switch (op) {
+        case 0: r = r_round1(x[i]); break;
+        case 1: r = r_round1_exact(x[i]); break;
+        case 2: r = exp_tab(x[i], tab); break;
+        case 3: r = div_fast(x[i], y[i]); break;
+        case 4: r = rcbrt_fast(x[i]); break;
+        default: r = r_round_dig(x[i], (int)y[i]); break;
+    }
+    out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return GR2M_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return GR2M_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+struct gr2m_basin {
+    int device = 0, ntime = 0, ntime_pad = 0, ncell = 0, ncell_pad = 0, ntiles = 0, nreg = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    DevBuf F, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
+    double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
+    int qobs_n = 0;
+};
+
+static void basin_free(gr2m_basin *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    DevBuf *bufs[] = {&b->F, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
+                      &b->crit, &b->qobs, &b->sim_out, &b->sim_t, &b->s0, &b->r0, &b->send, &b->rend};
+    for (DevBuf *d : bufs) d->release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    free(b->qobs_host_copy);
+    delete b;
+}
+
+extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const double *E, const double *area,
+                                 const int *ndays, const int *region_id, int nreg, gr2m_basin **out)
+{
+    REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    REQUIRE(ntime > 0 && ncell > 0 && nreg > 0, "ntime, ncell and nreg must be positive");
+    REQUIRE(P && E && area && ndays && region_id, "NULL input array");
+    for (int c = 0; c < ncell; ++c) REQUIRE(region_id[c] >= 0 && region_id[c] < nreg, "region_id out of range");
+    for (int t = 0; t < ntime; ++t) REQUIRE(ndays[t] > 0, "ndays must be positive");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    gr2m_basin *b = new (std::nothrow) gr2m_basin();
+    if (!b) { gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
+    b->device = g_device;
+    b->ntime = ntime; b->ncell = ncell; b->nreg = nreg;
+    b->ntime_pad = ceil_div(ntime, TM) * TM;
+    b->ntiles = ceil_div(ncell, 32);
+    b->ncell_pad = b->ntiles * 32;
+#define BCK(call) do { int rc_ = (call); if (rc_) { basin_free(b); return rc_; } } while (0)
+#define BCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); basin_free(b); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+    BCU(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    b->stream = b->own_stream;
+    BCU(cudaEventCreate(&b->ev0));
+    BCU(cudaEventCreate(&b->ev1));
+    size_t nraw = (size_t)ncell * ntime * sizeof(double);
+    BCK(b->F.ensure((size_t)b->ntiles * b->ntime_pad * 64 * sizeof(double)));
+    BCK(b->area.ensure(ncell * sizeof(double)));
+    BCK(b->region.ensure(ncell * sizeof(int)));
+    BCK(b->den.ensure(ntime * sizeof(double)));
+    BCK(b->conv.ensure(ntime * sizeof(double)));
+    DevBuf rawP, rawE;
+    int r1 = rawP.ensure(nraw), r2 = rawE.ensure(nraw);
+    if (r1 || r2) { rawP.release(); rawE.release(); basin_free(b); return r1 ? r1 : r2; }
+    double *den = (double *)malloc(2 * ntime * sizeof(double));
+    if (!den) { rawP.release(); rawE.release(); basin_free(b); gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
+    for (int t = 0; t < ntime; ++t) { den[t] = 86.4 * (double)ndays[t]; den[ntime + t] = 1.0 / den[t]; }
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaMemcpyAsync(rawP.p, P, nraw, cudaMemcpyHostToDevice, b->stream));
+    step(cudaMemcpyAsync(rawE.p, E, nraw, cudaMemcpyHostToDevice, b->stream));
+    step(cudaMemcpyAsync(b->area.p, area, ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    step(cudaMemcpyAsync(b->region.p, region_id, ncell * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    step(cudaMemcpyAsync(b->den.p, den, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    step(cudaMemcpyAsync(b->conv.p, den + ntime, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    if (e == cudaSuccess) {
+        dim3 grid(b->ntiles, ceil_div(b->ntime_pad, 32)), blk(32, 8);
+        k_tile_forcing<<<grid, blk, 0, b->stream>>>(rawP.as<double>(), rawE.as<double>(), ncell, ntime, b->ntime_pad,
+                                                   b->F.as<double>());
+        step(cudaGetLastError());
+    }
+    step(cudaStreamSynchronize(b->stream));
+    free(den);
+    rawP.release(); rawE.release();
+    if (e != cudaSuccess) {
+        gr2m_set_error("gr2m_basin_create: upload failed: %s", cudaGetErrorString(e));
+        basin_free(b);
+        return GR2M_ERR_CUDA;
+    }
+    *out = b;
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_basin_destroy(gr2m_basin *b)
+{
+    basin_free(b);
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_basin_set_stream(gr2m_basin *b, void *cuda_stream)
+{
+    REQUIRE(b != nullptr, "handle is NULL");
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_basin_last_kernel_ms(gr2m_basin *b, float *ms)
+{
+    REQUIRE(b && ms, "NULL argument");
+    REQUIRE(b->timed, "no timed call yet");
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, const double *R0, int flags,
+                        double *PR, double *AE, double *SM, double *RU, double *QS, double *S_end, double *R_end)
+{
+    REQUIRE(b && params, "NULL handle or params");
+    REQUIRE((S0 == nullptr) == (R0 == nullptr), "S0 and R0 must both be given or both be NULL");
+    CK(cudaSetDevice(b->device));
+    const size_t plane = (size_t)b->ntime * b->ncell_pad;
+    int rc;
+    if ((rc = b->params.ensure(4 * b->nreg * sizeof(double)))) return rc;
+    if ((rc = b->sim_out.ensure(5 * plane * sizeof(double)))) return rc;
+    if ((rc = b->sim_t.ensure((size_t)b->ncell * b->ntime * sizeof(double)))) return rc;
+    if ((rc = b->send.ensure(b->ncell * sizeof(double)))) return rc;
+    if ((rc = b->rend.ensure(b->ncell * sizeof(double)))) return rc;
+    CK(cudaMemcpyAsync(b->params.p, params, 4 * b->nreg * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    if (S0) {
+        if ((rc = b->s0.ensure(b->ncell * sizeof(double)))) return rc;
+        if ((rc = b->r0.ensure(b->ncell * sizeof(double)))) return rc;
+        CK(cudaMemcpyAsync(b->s0.p, S0, b->ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->r0.p, R0, b->ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    }
+    SimArgs a;
+    a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = b->params.as<double>();
+    a.den = b->den.as<double>(); a.S0 = S0 ? b->s0.as<double>() : nullptr; a.R0 = R0 ? b->r0.as<double>() : nullptr;
+    a.region = b->region.as<int>(); a.out = b->sim_out.as<double>();
+    a.S_end = b->send.as<double>(); a.R_end = b->rend.as<double>();
+    a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad;
+    a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
+    CK(cudaEventRecord(b->ev0, b->stream));
+    int grid = ceil_div(b->ncell_pad, 128);
+    if (flags & GR2M_MATH_LITERAL) k_gr2m_sim<false><<<grid, 128, 0, b->stream>>>(a);
+    else k_gr2m_sim<true><<<grid, 128, 0, b->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, b->stream));
+    b->timed = true;
+    double *outs[5] = {PR, AE, SM, RU, QS};
+    for (int v = 0; v < 5; ++v) {
+        if (!outs[v]) continue;
+        dim3 g(ceil_div(b->ncell, 32), ceil_div(b->ntime, 32)), blk(32, 8);
+        k_transpose<<<g, blk, 0, b->stream>>>(b->sim_out.as<double>() + v * plane, b->ntime, b->ncell, b->ncell_pad,
+                                              b->sim_t.as<double>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(outs[v], b->sim_t.p, (size_t)b->ncell * b->ntime * sizeof(double), cudaMemcpyDeviceToHost,
+                           b->stream));
+    }
+    if (S_end) CK(cudaMemcpyAsync(S_end, b->send.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (R_end) CK(cudaMemcpyAsync(R_end, b->rend.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_run_once(int ntime, int ncell, const double *P, const double *E, const double *area,
+                             const int *ndays, const int *region_id, int nreg, const double *params,
+                             const double *S0, const double *R0, int flags, double *PR, double *AE, double *SM,
+                             double *RU, double *QS, double *S_end, double *R_end)
+{
+    gr2m_basin *b = nullptr;
+    int rc = gr2m_basin_create(ntime, ncell, P, E, area, ndays, region_id, nreg, &b);
+    if (rc) return rc;
+    rc = gr2m_run(b, params, S0, R0, flags, PR, AE, SM, RU, QS, S_end, R_end);
+    gr2m_basin_destroy(b);
+    return rc;
+}
+
+static int g_sm_count = 0;
+
+static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, const double *qobs, int warmup,
+                            int which, int flags, double *of_dev, double *crit_dev, double *qt_dev)
+{
+    int rc;
+    if (!g_sm_count) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, b->device));
+        g_sm_count = prop.multiProcessorCount;
+    }
+    // qobs -> device (cached: re-uploaded only when the host values change)
+    const bool has_obs = qobs != nullptr;
+    if (has_obs) {
+        bool same = b->qobs_host_copy && b->qobs_n == b->ntime &&
+                    memcmp(b->qobs_host_copy, qobs, b->ntime * sizeof(double)) == 0;
+        if (!same) {
+            if ((rc = b->qobs.ensure(b->ntime * sizeof(double)))) return rc;
+            free(b->qobs_host_copy);
+            b->qobs_host_copy = (double *)malloc(b->ntime * sizeof(double));
+            if (!b->qobs_host_copy) { gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
+            memcpy(b->qobs_host_copy, qobs, b->ntime * sizeof(double));
+            b->qobs_n = b->ntime;
+            CK(cudaMemcpyAsync(b->qobs.p, b->qobs_host_copy, b->ntime * sizeof(double), cudaMemcpyHostToDevice,
+                               b->stream));
+        }
+    }
+    // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
+    const int nsg = ceil_div(nsets, SPB);
+    const int target = g_sm_count * 3 * 8;
+    int csplit = ceil_div(target, nsg);
+    if (csplit > b->ntiles) csplit = b->ntiles;
+    if (csplit < 1) csplit = 1;
+    int tiles_per_split = ceil_div(b->ntiles, csplit);
+    csplit = ceil_div(b->ntiles, tiles_per_split);
+    if ((rc = b->partial.ensure((size_t)csplit * nsets * b->ntime * sizeof(double)))) return rc;
+    if (!qt_dev) {
+        if ((rc = b->qt.ensure((size_t)nsets * b->ntime * sizeof(double)))) return rc;
+        qt_dev = b->qt.as<double>();
+    }
+    const bool fast = !(flags & GR2M_MATH_LITERAL);
+    CalibArgs a;
+    a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = params_dev;
+    a.tconv = fast ? b->conv.as<double>() : b->den.as<double>();
+    a.region = b->region.as<int>(); a.partial = b->partial.as<double>();
+    a.ncell = b->ncell; a.ntiles = b->ntiles; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad; a.nreg = b->nreg;
+    a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
+    a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
+    size_t smem = (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
+    REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
+    auto kern = fast ? k_gr2m_calib<true> : k_gr2m_calib<false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaEventRecord(b->ev0, b->stream));
+    kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, b->stream));
+    ObjArgs o;
+    o.partial = b->partial.as<double>(); o.qobs = has_obs ? b->qobs.as<double>() : nullptr;
+    o.qt = qt_dev; o.of = of_dev; o.crit = crit_dev;
+    o.csplit = csplit; o.nsets = nsets; o.ntime = b->ntime; o.warmup = warmup < 0 ? 0 : warmup; o.which = which;
+    o.single_cell = b->ncell == 1; o.unrounded = (flags & GR2M_SINK_UNROUNDED) ? 1 : 0; o.has_obs = has_obs;
+    k_objective<<<ceil_div((long long)nsets * 32, 128), 128, 0, b->stream>>>(o);
+    CK(cudaGetLastError());
+    b->timed = true;
+    return GR2M_OK;
+}
+
+extern "C" int gr2m_objective_batch_dev(gr2m_basin *b, const double *params_dev, int nsets, const double *qobs,
+                                        int warmup, int which, int flags, double *out_of_dev,
+                                        double *out_crit_dev, double *out_qt_dev)
+{
+    REQUIRE(b && params_dev, "NULL handle or params");
+    REQUIRE(nsets > 0, "nsets must be positive");
+    REQUIRE(which >= 0 && which <= 2, "which must be GR2M_OF_KGE, _NSE or _RMSE");
+    REQUIRE(warmup < b->ntime, "warmup must be smaller than ntime");
+    CK(cudaSetDevice(b->device));
+    return launch_objective(b, params_dev, nsets, qobs, warmup, which, flags, out_of_dev, out_crit_dev, out_qt_dev);
+}
+
+extern "C" int gr2m_objective_batch(gr2m_basin *b, const double *params, int nsets, const double *qobs, int warmup,
+                                    int which, int flags, double *out_of, double *out_crit, double *out_qt)
+{
+    REQUIRE(b && params, "NULL handle or params");
+    REQUIRE(nsets > 0, "nsets must be positive");
+    REQUIRE(which >= 0 && which <= 2, "which must be GR2M_OF_KGE, _NSE or _RMSE");
+    REQUIRE(warmup < b->ntime, "warmup must be smaller than ntime");
+    REQUIRE(qobs || out_qt, "nothing to compute: qobs and out_qt are both NULL");
+    CK(cudaSetDevice(b->device));
+    int rc;
+    const size_t np = (size_t)nsets * 4 * b->nreg;
+    if ((rc = b->params.ensure(np * sizeof(double)))) return rc;
+    if ((rc = b->of.ensure(nsets * sizeof(double)))) return rc;
+    if ((rc = b->crit.ensure((size_t)nsets * 3 * sizeof(double)))) return rc;
+    if ((rc = b->qt.ensure((size_t)nsets * b->ntime * sizeof(double)))) return rc;
+    CK(cudaMemcpyAsync(b->params.p, params, np * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    rc = launch_objective(b, b->params.as<double>(), nsets, qobs, warmup, which, flags, b->of.as<double>(),
+                          b->crit.as<double>(), b->qt.as<double>());
+    if (rc) return rc;
+    if (out_of && qobs) CK(cudaMemcpyAsync(out_of, b->of.p, nsets * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (out_crit && qobs)
+        CK(cudaMemcpyAsync(out_crit, b->crit.p, (size_t)nsets * 3 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (out_qt)
+        CK(cudaMemcpyAsync(out_qt, b->qt.p, (size_t)nsets * b->ntime * sizeof(double), cudaMemcpyDeviceToHost,
+                           b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return GR2M_OK;
+}
+
+// FP64 pipe peak: 8 independent DFMA chains per thread, no memory traffic.  Returns TFLOP/s
+// (2 flop per DFMA).  The roofline denominator for the recursion kernel, measured in place.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double *sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;
+}
+
+extern "C" int gr2m_fp64_peak(int iters, double *tflops, float *ms_out)
+{
+    REQUIRE(iters > 0 && tflops, "bad arguments");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    const int blocks = prop.multiProcessorCount * 8;
+    double *sink = nullptr;
+    CK(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, 256>>>(iters, 1.0, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = 2.0 * 64.0 * (double)iters * 256.0 * blocks / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return GR2M_OK;
+}
+
+// test hook (declared in tests only): element-wise device math, see k_debug_math
+extern "C" int gr2m_debug_math(int op, int n, const double *x, const double *y, double *out)
+{
+    REQUIRE(n > 0 && x && out, "bad arguments");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dx, n * sizeof(double)));
+    CK(cudaMalloc(&dy, n * sizeof(double)));
+    CK(cudaMalloc(&dout, n * sizeof(double)));
+    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (y) CK(cudaMemcpy(dy, y, n * sizeof(double), cudaMemcpyHostToDevice));
+    else CK(cudaMemset(dy, 0, n * sizeof(double)));
+    k_debug_math<<<ceil_div(n, 256), 256>>>(op, n, dx, dy, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return GR2M_OK;
+}

@@ -1,0 +1,214 @@
+// gr2m_math.cuh -- FP64 device arithmetic of the GR2M step (sm_100a).
+//
+// Two formulations of the same month step (airGR frun_GR2M.f90 MOD_GR2M, reached
+// from R/Run_GR2MSemiDistr.R:181-184 and R/Optim_GR2MSemiDistr.R:174-177):
+//   step_literal : IEEE division, libdevice exp()/pow(), operation order as written in airGR.
+//   step_fast    : same algebra with the two tanh divisions folded into the store updates
+//                  (3 divisions instead of 12), a table-driven exp, a Halley-refined reciprocal cube
+//                  root and Newton-refined MUFU reciprocals.  Every building block is accurate to
+//                  ~1 ulp, so the two agree to ~1e-14 relative; tests hold both to 1e-10.
+// The forcing correction round(f*x, 1) (R/Run_GR2MSemiDistr.R:101-102) is BIT-EXACT in both: a wrong
+// rounding decision is a 0.1 mm error, not an ulp.
+#pragma once
+
+#include "common.cuh"
+
+// 2^(j/32), j = 0..31 (correctly rounded); copied to shared memory by the kernels that use exp_tab
+__constant__ double c_exp2_tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+#define GR2M_MAGIC 6755399441055744.0   /* 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51 */
+
+// ---- R round(x, 1) ------------------------------------------------------------------------------
+// Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
+__device__ __forceinline__ double div10_rn(double n)
+{
+    double q = __dmul_rn(n, 0.1);
+    double r = __fma_rn(-q, 10.0, n);
+    return __fma_rn(r, 0.1, q);
+}
+
+// R >= 4.0 algorithm verbatim: candidates floor/ceil(10x)/10, closer one wins in
+// double arithmetic, even last digit on a tie.  Any finite or non-finite x.
+__device__ __noinline__ double r_round1_exact(double x)
+{
+    double a = fabs(x);
+    if (!(a < 1e14) || a == 0.0) return x;
+    double x10 = __dmul_rn(10.0, a);
+    double i10 = floor(x10);
+    double xd = div10_rn(i10), xu = div10_rn(ceil(x10));
+    double du = __dsub_rn(xu, a), dd = __dsub_rn(a, xd);
+    bool even = __dsub_rn(i10, __dmul_rn(2.0, floor(__dmul_rn(0.5, i10)))) == 0.0;
+    double r = (dd < du || (dd == du && even)) ? xd : xu;
+    return copysign(r, x);
+}
+
+// Same result, cheap common case: away from a decimal tie the winner is rint(10x)/10.
+__device__ __forceinline__ double r_round1(double x)
+{
+    double x10 = __dmul_rn(x, 10.0);
+    double n = __dadd_rn(__dadd_rn(x10, GR2M_MAGIC), -GR2M_MAGIC);
+    double f = __dsub_rn(x10, n);
+    if (!(fabs(f) < 0.499 && x >= 0.0 && x10 < 1e15)) return r_round1_exact(x);
+    return div10_rn(n);
+}
+
+// general digits (1..3 used), IEEE division; for the objective kernel (not hot)
+__device__ double r_round_dig(double x, int dig)
+{
+    double a = fabs(x);
+    if (!(a < 1.7e308) || a == 0.0) return x;      // NaN, Inf, 0
+    int e10 = (int)floor(log10(a)) + 1;
+    if (dig + e10 > 15) return x;
+    double p10 = dig == 1 ? 10.0 : (dig == 2 ? 100.0 : 1000.0);
+    double x10 = __dmul_rn(p10, a);
+    double i10 = floor(x10);
+    double xd = __ddiv_rn(i10, p10), xu = __ddiv_rn(ceil(x10), p10);
+    double du = __dsub_rn(xu, a), dd = __dsub_rn(a, xd);
+    bool even = fmod(i10, 2.0) == 0.0;
+    double r = (dd < du || (dd == du && even)) ? xd : xu;
+    return copysign(r, x);
+}
+
+// ---- fast building blocks -----------------------------------------------------------------------
+// exp(x) for moderate |x| (here 0 <= x <= 26): k = rint(32 x / ln2), r = x - k ln2/32 (|r| <= ln2/64),
+// exp(x) = 2^(k>>5) * 2^((k&31)/32) * (1 + r + ... + r^6/720); truncation 3.5e-18, total ~1 ulp.
+__device__ __forceinline__ double exp_tab(double x, const double *__restrict__ tab)
+{
+    double t = __fma_rn(x, 0x1.71547652b82fep+5, GR2M_MAGIC);
+    int ki = __double2loint(t);
+    double kd = __dadd_rn(t, -GR2M_MAGIC);
+    double r = __fma_rn(kd, -0x1.62e42ff000000p-6, x);
+    r = __fma_rn(kd, 0x1.718432a1b0e26p-40, r);
+    double p = 0x1.6c16c16c16c17p-10;
+    p = __fma_rn(p, r, 0x1.1111111111111p-7);
+    p = __fma_rn(p, r, 0x1.5555555555555p-5);
+    p = __fma_rn(p, r, 0x1.5555555555555p-3);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    double v = __dmul_rn(p, tab[ki & 31]);
+    return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
+}
+
+__device__ __forceinline__ double rcp_seed(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+}
+
+// n / d for normal-range d (denominators here are >= 2): MUFU seed, one Newton step on the
+// reciprocal, one residual correction on the quotient -> ~0.5-1 ulp.
+__device__ __forceinline__ double div_fast(double n, double d)
+{
+    double r = rcp_seed(d);
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    double q = __dmul_rn(n, r);
+    double rem = __fma_rn(-d, q, n);
+    return __fma_rn(rem, r, q);
+}
+
+// c^(-1/3) for c in [1, 2] (works for any normal c > 0): FP32 MUFU seed (~2^-21), one Halley step
+// y <- y + y e (1/3 + 2/9 e), e = 1 - c y^3   (cubic: residual ~ e^3)
+__device__ __forceinline__ double rcbrt_fast(double c)
+{
+    float cf = __double2float_rn(c);
+    float l, y0;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(cf));
+    l *= -0.333333343f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(l));
+    double y = (double)y0;
+    double y3 = __dmul_rn(__dmul_rn(y, y), y);
+    double e = __fma_rn(-c, y3, 1.0);
+    double q = __fma_rn(e, 0x1.c71c71c71c71cp-3, 0x1.5555555555555p-2);
+    return __fma_rn(__dmul_rn(y, e), q, y);
+}
+
+// ---- the month step -----------------------------------------------------------------------------
+struct CellPar {
+    double X1, X2, iX1, fp, fe, area;
+};
+
+struct StepOut {
+    double Pc, AE, Q;   // corrected precipitation, actual evaporation, runoff [mm]; S, R updated in place
+};
+
+#define GR2M_F32_EXP_DELTA 9.9341074625651041667e-9   /* (double)(1.f/3.f) - 1/3 */
+
+__device__ __forceinline__ StepOut step_fast(const CellPar &p, double Praw, double Eraw, double &S, double &R,
+                                             bool f32exp, const double *__restrict__ tab)
+{
+    StepOut o;
+    double Pc = r_round1(__dmul_rn(p.fp, Praw));
+    double Ec = r_round1(__dmul_rn(p.fe, Eraw));
+    // production store: S1 = (S + X1 T)/(1 + S/X1 T), T = tanh(w) = (a-1)/(a+1), a = exp(2w)
+    double w = fmin(Pc * p.iX1, 13.0);
+    double a = exp_tab(w + w, tab);
+    double am1 = a - 1.0, ap1 = a + 1.0;
+    double s = S * p.iX1;
+    double S1 = div_fast(__fma_rn(p.X1, am1, S * ap1), __fma_rn(s, am1, ap1));
+    double P1 = (Pc + S) - S1;
+    // evaporation: S2 = S1 (1-T)/(1 + (1 - S1/X1) T) = 2 S1 / ((b+1) + (1 - S1/X1)(b-1)), b = exp(2w)
+    w = fmin(Ec * p.iX1, 13.0);
+    double b = exp_tab(w + w, tab);
+    double s1 = S1 * p.iX1;
+    double S2 = div_fast(S1 + S1, __fma_rn(1.0 - s1, b - 1.0, b + 1.0));
+    o.AE = S1 - S2;
+    // percolation: S = S2 / (1 + (S2/X1)^3)^(1/3)
+    double sr = S2 * p.iX1;
+    double c = __fma_rn(sr * sr, sr, 1.0);
+    double y = rcbrt_fast(c);
+    if (f32exp) y = __fma_rn(-GR2M_F32_EXP_DELTA * (double)__logf(__double2float_rn(c)), y, y);
+    S = S2 * y;
+    // routing store with exchange: R2 = X2 (R + P1 + P2), Q = R2^2/(R2 + 60)
+    double R2 = p.X2 * (R + (P1 + (S2 - S)));
+    double Q = div_fast(R2 * R2, R2 + 60.0);
+    R = R2 - Q;
+    o.Pc = Pc;
+    o.Q = Q;
+    return o;
+}
+
+__device__ __forceinline__ StepOut step_literal(const CellPar &p, double Praw, double Eraw, double &S,
+                                                double &R, bool f32exp)
+{
+    StepOut o;
+    double Pc = r_round1_exact(__dmul_rn(p.fp, Praw));
+    double Ec = r_round1_exact(__dmul_rn(p.fe, Eraw));
+    double WS = Pc / p.X1;
+    if (WS > 13.0) WS = 13.0;
+    double ev = exp(WS);
+    double T = (ev - 1.0 / ev) / (ev + 1.0 / ev);
+    double Sr = S / p.X1;
+    double S1 = (S + p.X1 * T) / (1.0 + Sr * T);
+    double P1 = Pc + S - S1;
+    WS = Ec / p.X1;
+    if (WS > 13.0) WS = 13.0;
+    ev = exp(WS);
+    T = (ev - 1.0 / ev) / (ev + 1.0 / ev);
+    double S2 = S1 * (1.0 - T) / (1.0 + (1.0 - S1 / p.X1) * T);
+    o.AE = S1 - S2;
+    Sr = S2 / p.X1;
+    Sr = Sr * Sr * Sr + 1.0;
+    S = S2 / pow(Sr, f32exp ? (double)(1.0f / 3.0f) : 1.0 / 3.0);
+    double P2 = S2 - S;
+    double P3 = P1 + P2;
+    double R1 = R + P3;
+    double R2 = p.X2 * R1;
+    double Q = R2 * R2 / (R2 + 60.0);
+    R = R2 - Q;
+    o.Pc = Pc;
+    o.Q = Q;
+    return o;
+}

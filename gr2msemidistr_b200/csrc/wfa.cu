@@ -1,0 +1,760 @@
+// wfa.cu -- Weighted Flow Accumulation (TauDEM "AreaD8 -wg" semantics) on a D8 grid, all months
+// batched, and its C ABI (sm_100a).  Replaces the month loop of R/Routing_GR2MSemiDistr.R:100-123.
+//
+// Plan (month-invariant, built once on the device, integer, deterministic):
+//   receiver[c], inmask[c] (bit k-1: neighbour k drains into c), indeg[c], level[c] (Kahn frontier
+//   index), order[] = cells sorted by (level, cell id), level_off[], contam[c] (TauDEM edge
+//   contamination, which depends on topology only).
+// Sweep: accumulation buffer A[cell][ld] is cell-major with the month batch contiguous, so one
+// sub-warp group handles one cell with the months on its lanes: every upstream row is one coalesced
+// read, and a cell's sum is taken in TauDEM's fixed k = 1..8 neighbour order -- deterministic with
+// no atomics and no cross-lane reduction.  Cells of one level are independent; levels are
+// swept in order: wide levels as one launch each, the long thin tail by a single resident CTA
+// (level-synchronous mode) or by a flag-driven dataflow kernel (default).
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+namespace {
+
+__constant__ int c_dx[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int c_dy[9] = {0, 0, -1, -1, -1, 0, 1, 1, 1};
+
+__device__ __forceinline__ bool d8_valid(int d) { return d >= 1 && d <= 8; }
+
+// ---- plan construction --------------------------------------------------------------------------
+__global__ void k_topology(const int16_t *__restrict__ dir, int nrow, int ncol, int32_t *__restrict__ receiver,
+                           uint8_t *__restrict__ inmask, int32_t *__restrict__ indeg, int32_t *__restrict__ cnt,
+                           uint8_t *__restrict__ contam, int32_t *__restrict__ level)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nrow * ncol) return;
+    int r = (int)(i / ncol), c = (int)(i % ncol);
+    int d = dir[i];
+    level[i] = -1;
+    if (!d8_valid(d)) {
+        receiver[i] = -1; inmask[i] = 0; indeg[i] = 0; cnt[i] = -1; contam[i] = 0;
+        return;
+    }
+    int rr = r + c_dy[d], cc = c + c_dx[d];
+    int32_t rec = -1;
+    if (rr >= 0 && rr < nrow && cc >= 0 && cc < ncol && d8_valid(dir[(long long)rr * ncol + cc]))
+        rec = (int32_t)((long long)rr * ncol + cc);
+    unsigned m = 0, edge = 0;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+        int r2 = r + c_dy[k], c2 = c + c_dx[k];
+        if (r2 < 0 || r2 >= nrow || c2 < 0 || c2 >= ncol) { edge = 1; continue; }
+        int dn = dir[(long long)r2 * ncol + c2];
+        if (!d8_valid(dn)) { edge = 1; continue; }
+        if (dn - k == 4 || dn - k == -4) m |= 1u << (k - 1);
+    }
+    receiver[i] = rec; inmask[i] = (uint8_t)m; indeg[i] = __popc(m); cnt[i] = __popc(m);
+    contam[i] = (uint8_t)edge;   // seeded with the cell's own edge flag; upstream OR-ed in while peeling
+}
+
+__global__ void k_frontier_init(const int32_t *__restrict__ cnt, long long n, int32_t *__restrict__ frontier,
+                                int *__restrict__ count)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && cnt[i] == 0) frontier[atomicAdd(count, 1)] = (int32_t)i;
+}
+
+__device__ __forceinline__ void peel_cell(int32_t c, int lev, int ncol, const int32_t *__restrict__ receiver,
+                                          const uint8_t *__restrict__ inmask, int32_t *cnt, uint8_t *contam,
+                                          int32_t *level, int32_t *next, int *next_count)
+{
+    level[c] = lev;
+    unsigned m = inmask[c], con = contam[c];
+    while (m) {
+        int k = __ffs(m);   // 1-based bit index == neighbour k
+        m &= m - 1;
+        con |= ((volatile uint8_t *)contam)[c + c_dy[k] * ncol + c_dx[k]];
+    }
+    contam[c] = (uint8_t)con;
+    int32_t d = receiver[c];
+    if (d >= 0 && atomicSub(&cnt[d], 1) == 1) next[atomicAdd(next_count, 1)] = d;
+}
+
+// one Kahn frontier per launch (wide frontiers)
+__global__ void k_peel(const int32_t *__restrict__ cur, int ncur, int lev, int ncol,
+                       const int32_t *__restrict__ receiver, const uint8_t *__restrict__ inmask, int32_t *cnt,
+                       uint8_t *contam, int32_t *level, int32_t *next, int *next_count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncur) peel_cell(cur[i], lev, ncol, receiver, inmask, cnt, contam, level, next, next_count);
+}
+
+// many thin frontiers inside one resident CTA; stops when the frontier is empty or wider than `limit`
+// state[0] = level, state[1] = frontier size, state[2] = which buffer holds the frontier (0/1)
+__global__ void __launch_bounds__(1024) k_peel_thin(int32_t *buf0, int32_t *buf1, int *state, int limit, int ncol,
+                                                    const int32_t *__restrict__ receiver,
+                                                    const uint8_t *__restrict__ inmask, int32_t *cnt, uint8_t *contam,
+                                                    int32_t *level)
+{
+    __shared__ int s_next;
+    int lev = state[0], n = state[1], which = state[2];
+    while (n > 0 && n <= limit) {
+        int32_t *cur = which ? buf1 : buf0, *nxt = which ? buf0 : buf1;
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            peel_cell(cur[i], lev, ncol, receiver, inmask, cnt, contam, level, nxt, &s_next);
+        __threadfence();
+        __syncthreads();
+        n = s_next;
+        which ^= 1;
+        ++lev;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { state[0] = lev; state[1] = n; state[2] = which; }
+}
+
+__global__ void k_sort_keys(const int32_t *__restrict__ level, long long n, int nlevels, uint32_t *__restrict__ keys,
+                            int32_t *__restrict__ vals)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = level[i];
+    keys[i] = l < 0 ? (uint32_t)nlevels : (uint32_t)l;
+    vals[i] = (int32_t)i;
+}
+
+__global__ void k_level_offsets(const uint32_t *__restrict__ keys, long long n, int nlevels,
+                                int32_t *__restrict__ level_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = keys[i];
+    if (k >= (uint32_t)nlevels) {
+        if (i == 0 || keys[i - 1] < (uint32_t)nlevels) level_off[nlevels] = (int32_t)i;
+        return;
+    }
+    if (i == 0 || keys[i - 1] != k) level_off[k] = (int32_t)i;
+    if (i == n - 1) level_off[nlevels] = (int32_t)n;
+}
+
+// tailmask[c]: bit k-1 set iff upstream neighbour k of c lies in the tail (level >= tail_level)
+__global__ void k_tailmask(const int32_t *__restrict__ order, int begin, int end, int ncol, int tail_level,
+                           const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level,
+                           uint8_t *__restrict__ tailmask)
+{
+    int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    int32_t c = order[i];
+    unsigned m = inmask[c], tm = 0;
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        if (level[c + c_dy[k] * ncol + c_dx[k]] >= tail_level) tm |= 1u << (k - 1);
+    }
+    tailmask[c] = (uint8_t)tm;
+}
+
+// ---- sweep --------------------------------------------------------------------------------------
+// One group of G lanes per cell, months j = g, g+G, ... on the lanes.
+// CG: read through L2 only (rows written by other SMs / warps during the same launch).
+template <typename T, int G, bool CG>
+__device__ __forceinline__ void accum_cell(int32_t c, int g, int ncol, unsigned m, T *A, int ld, int nmonth)
+{
+    T *row = A + (size_t)c * ld;
+    for (int j = g; j < nmonth; j += G) {
+        T acc = CG ? __ldcg(row + j) : row[j];
+        unsigned mm = m;
+        while (mm) {
+            int k = __ffs(mm);
+            mm &= mm - 1;
+            const T *up = A + (size_t)(c + c_dy[k] * ncol + c_dx[k]) * ld + j;
+            acc += CG ? __ldcg(up) : *up;
+        }
+        row[j] = acc;
+    }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256) k_accum_level(const int32_t *__restrict__ order, int begin, int end, int ncol,
+                                                     const uint8_t *__restrict__ inmask, T *__restrict__ A, int ld,
+                                                     int nmonth)
+{
+    int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, g = threadIdx.x % G;
+    int i = begin + gid;
+    if (i >= end) return;
+    int32_t c = order[i];
+    unsigned m = inmask[c];
+    if (m) accum_cell<T, G, false>(c, g, ncol, m, A, ld, nmonth);
+}
+
+// thin levels [lev0, lev1) inside one resident CTA, a block barrier between levels
+template <typename T, int G>
+__global__ void __launch_bounds__(1024) k_accum_thin(const int32_t *__restrict__ order,
+                                                     const int32_t *__restrict__ level_off, int lev0, int lev1,
+                                                     int ncol, const uint8_t *__restrict__ inmask, T *A, int ld,
+                                                     int nmonth)
+{
+    const int ngroups = blockDim.x / G, gid = threadIdx.x / G, g = threadIdx.x % G;
+    for (int l = lev0; l < lev1; ++l) {
+        int b = level_off[l], e = level_off[l + 1];
+        for (int i = b + gid; i < e; i += ngroups) {
+            int32_t c = order[i];
+            unsigned m = inmask[c];
+            if (m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
+        }
+        __syncthreads();
+    }
+}
+
+// dataflow tail: cells order[begin, end) are claimed in order, one ticket per sub-warp group and
+// CHUNK cells per ticket; a cell waits only for tail upstream cells (tailmask) to publish their
+// epoch in done[], which are always held by earlier tickets => no deadlock.
+template <typename T, int G>
+__global__ void __launch_bounds__(256) k_accum_dataflow(const int32_t *__restrict__ order, int begin, int end,
+                                                        int ncol, const uint8_t *__restrict__ inmask,
+                                                        const uint8_t *__restrict__ tailmask, T *A, int ld, int nmonth,
+                                                        unsigned *done, unsigned epoch, int *ticket)
+{
+    constexpr int CHUNK = 4;
+    const int g = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
+    for (;;) {
+        int t0 = 0;
+        if (g == 0) t0 = atomicAdd(ticket, CHUNK);
+        t0 = __shfl_sync(gmask, t0, (threadIdx.x % 32) / G * G);
+        int i0 = begin + t0;
+        if (i0 >= end) return;
+        int i1 = min(end, i0 + CHUNK);
+        for (int i = i0; i < i1; ++i) {
+            int32_t c = order[i];
+            unsigned m = inmask[c], tm = tailmask[c];
+            if (g == 0) {
+                while (tm) {
+                    int k = __ffs(tm);
+                    tm &= tm - 1;
+                    const volatile unsigned *f = done + (c + c_dy[k] * ncol + c_dx[k]);
+                    while (*f != epoch) { }
+                }
+                __threadfence();
+            }
+            __syncwarp(gmask);
+            if (m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
+            __syncwarp(gmask);
+            if (g == 0) {
+                __threadfence();
+                ((volatile unsigned *)done)[c] = epoch;
+            }
+        }
+    }
+}
+
+// contaminated / unreached / nodata cells -> NaN
+template <typename T>
+__global__ void k_mask(const int32_t *__restrict__ level, const uint8_t *__restrict__ contam, int use_contam,
+                       long long ncell, T *A, int ld, int nmonth)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long c = idx / nmonth;
+    int j = (int)(idx % nmonth);
+    if (c >= ncell) return;
+    if (level[c] < 0 || (use_contam && contam[c])) A[(size_t)c * ld + j] = (T)NAN;
+}
+
+// planes [nmonth][ncell] (double) -> cell-major [ncell][ld] (T) and back
+template <typename T>
+__global__ void k_planes_to_cells(const double *__restrict__ in, long long ncell, int nmonth, int ld, T *__restrict__ out)
+{
+    __shared__ double s[32][33];
+    long long c0 = (long long)blockIdx.x * 32;
+    int m0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long c = c0 + threadIdx.x;
+        int m = m0 + j;
+        s[j][threadIdx.x] = (c < ncell && m < nmonth) ? in[(size_t)m * ncell + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long c = c0 + j;
+        int m = m0 + threadIdx.x;
+        if (c < ncell && m < ld) out[(size_t)c * ld + m] = (T)s[threadIdx.x][j];
+    }
+}
+
+template <typename T>
+__global__ void k_cells_to_planes(const T *__restrict__ in, long long ncell, int nmonth, int ld, double *__restrict__ out)
+{
+    __shared__ double s[32][33];
+    long long c0 = (long long)blockIdx.x * 32;
+    int m0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long c = c0 + j;
+        int m = m0 + threadIdx.x;
+        s[j][threadIdx.x] = (c < ncell && m < nmonth) ? (double)in[(size_t)c * ld + m] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long c = c0 + threadIdx.x;
+        int m = m0 + j;
+        if (c < ncell && m < nmonth) out[(size_t)m * ncell + c] = s[threadIdx.x][j];
+    }
+}
+
+// Weight[index$cells] <- QS[i,]  (Routing:109-113); src < 0 marks an overwritten duplicate
+template <typename T>
+__global__ void k_scatter(const double *__restrict__ QS, const int32_t *__restrict__ src, int nsub, int ntime, T *A, int ld)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = idx / ntime, t = idx % ntime;
+    if (s >= nsub || src[s] < 0) return;
+    A[(size_t)src[s] * ld + t] = (T)QS[(size_t)s * ntime + t];
+}
+
+// max(values[coverage_fraction == 1], na.rm = TRUE) per polygon and month (Routing:119-121).
+// Block = one polygon x 32 months; warps stride over the polygon's cells, then a shared-memory max.
+template <typename T>
+__global__ void __launch_bounds__(256) k_polygon_max(const int32_t *__restrict__ poff, const int32_t *__restrict__ pcells,
+                                                     const int32_t *__restrict__ level, const uint8_t *__restrict__ contam,
+                                                     int use_contam, const T *__restrict__ A, int ld, int ntime,
+                                                     double *__restrict__ QR)
+{
+    __shared__ double sm[8][32];
+    const int s = blockIdx.x, t = blockIdx.y * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    double m = -INFINITY;
+    if (t < ntime)
+        for (int q = poff[s] + w; q < poff[s + 1]; q += 8) {
+            int32_t c = pcells[q];
+            if (level[c] < 0 || (use_contam && contam[c])) continue;
+            double v = (double)A[(size_t)c * ld + t];
+            if (v > m) m = v;
+        }
+    sm[w][threadIdx.x & 31] = m;
+    __syncthreads();
+    if (w == 0 && t < ntime) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = fmax(m, sm[k][threadIdx.x]);
+        QR[(size_t)s * ntime + t] = m;
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return GR2M_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return GR2M_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+constexpr int THIN_LIMIT = 2048;      // plan peeling: frontiers this small are peeled inside one CTA
+constexpr int TAIL_WIDTH = 512;       // sweep: the tail starts where every later level is at most this wide
+
+}  // namespace
+
+struct wfa_plan {
+    int device = 0, nrow = 0, ncol = 0, nlevels = 0, norder = 0, tail_level = 0, flags = 0;
+    long long ncell = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    unsigned epoch = 0;
+    DevBuf receiver, inmask, indeg, level, order, level_off, contam, tailmask, done, ticket, work, work2, qs, src, poff,
+        pcells, qr;
+    std::vector<int32_t> h_level_off;
+};
+
+static void plan_free(wfa_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
+                      &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
+                      &p->qr};
+    for (DevBuf *d : bufs) d->release();
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+static int plan_build(wfa_plan *p, const int16_t *dir_dev)
+{
+    const long long n = p->ncell;
+    const int nb = ceil_div(n, 256);
+    int rc;
+    if ((rc = p->receiver.ensure(n * 4))) return rc;
+    if ((rc = p->inmask.ensure(n))) return rc;
+    if ((rc = p->indeg.ensure(n * 4))) return rc;
+    if ((rc = p->level.ensure(n * 4))) return rc;
+    if ((rc = p->contam.ensure(n))) return rc;
+    DevBuf cnt, f0, f1, state;
+    auto cleanup = [&]() { cnt.release(); f0.release(); f1.release(); state.release(); };
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+#define PRC(call) do { int r_ = (call); if (r_) { cleanup(); return r_; } } while (0)
+    PRC(cnt.ensure(n * 4));
+    PRC(f0.ensure(n * 4));
+    PRC(f1.ensure(n * 4));
+    PRC(state.ensure(4 * sizeof(int)));
+    cudaStream_t st = p->stream;
+    k_topology<<<nb, 256, 0, st>>>(dir_dev, p->nrow, p->ncol, p->receiver.as<int32_t>(), p->inmask.as<uint8_t>(),
+                                   p->indeg.as<int32_t>(), cnt.as<int32_t>(), p->contam.as<uint8_t>(),
+                                   p->level.as<int32_t>());
+    PCK(cudaGetLastError());
+    int *d_state = state.as<int>();   // [0] level [1] size [2] which [3] scratch counter
+    PCK(cudaMemsetAsync(d_state, 0, 4 * sizeof(int), st));
+    k_frontier_init<<<nb, 256, 0, st>>>(cnt.as<int32_t>(), n, f0.as<int32_t>(), d_state + 1);
+    PCK(cudaGetLastError());
+    int h[4] = {0, 0, 0, 0};
+    PCK(cudaMemcpyAsync(h, d_state, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    long long reached = 0;
+    while (h[1] > 0) {
+        if (h[1] > THIN_LIMIT) {
+            reached += h[1];
+            int32_t *cur = h[2] ? f1.as<int32_t>() : f0.as<int32_t>(), *nxt = h[2] ? f0.as<int32_t>() : f1.as<int32_t>();
+            PCK(cudaMemsetAsync(d_state + 3, 0, sizeof(int), st));
+            k_peel<<<ceil_div(h[1], 256), 256, 0, st>>>(cur, h[1], h[0], p->ncol, p->receiver.as<int32_t>(),
+                                                         p->inmask.as<uint8_t>(), cnt.as<int32_t>(),
+                                                         p->contam.as<uint8_t>(), p->level.as<int32_t>(), nxt, d_state + 3);
+            PCK(cudaGetLastError());
+            int nn = 0;
+            PCK(cudaMemcpyAsync(&nn, d_state + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCK(cudaStreamSynchronize(st));
+            h[0] += 1; h[1] = nn; h[2] ^= 1;
+        } else {
+            PCK(cudaMemcpyAsync(d_state, h, 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+            k_peel_thin<<<1, 1024, 0, st>>>(f0.as<int32_t>(), f1.as<int32_t>(), d_state, THIN_LIMIT, p->ncol,
+                                            p->receiver.as<int32_t>(), p->inmask.as<uint8_t>(), cnt.as<int32_t>(),
+                                            p->contam.as<uint8_t>(), p->level.as<int32_t>());
+            PCK(cudaGetLastError());
+            PCK(cudaMemcpyAsync(h, d_state, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCK(cudaStreamSynchronize(st));
+        }
+    }
+    p->nlevels = h[0];
+    cleanup();
+    // order = stable radix sort of cell ids by level (cells never reached sort last and are cut off)
+    DevBuf keys, keys2, vals, temp;
+    auto cleanup2 = [&]() { keys.release(); keys2.release(); vals.release(); temp.release(); };
+#undef PCK
+#undef PRC
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup2(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+#define PRC(call) do { int r_ = (call); if (r_) { cleanup2(); return r_; } } while (0)
+    PRC(keys.ensure(n * 4));
+    PRC(keys2.ensure(n * 4));
+    PRC(vals.ensure(n * 4));
+    PRC(p->order.ensure(n * 4));
+    PRC(p->level_off.ensure(((size_t)p->nlevels + 2) * 4));
+    k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>());
+    PCK(cudaGetLastError());
+    int bits = 1;
+    while ((1ll << bits) <= p->nlevels) ++bits;
+    size_t tbytes = 0;
+    PCK(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
+                                        p->order.as<int32_t>(), n, 0, bits, st));
+    PRC(temp.ensure(tbytes ? tbytes : 16));
+    PCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
+                                        p->order.as<int32_t>(), n, 0, bits, st));
+    PCK(cudaMemsetAsync(p->level_off.p, 0, ((size_t)p->nlevels + 2) * 4, st));
+    k_level_offsets<<<nb, 256, 0, st>>>(keys2.as<uint32_t>(), n, p->nlevels, p->level_off.as<int32_t>());
+    PCK(cudaGetLastError());
+    p->h_level_off.assign((size_t)p->nlevels + 1, 0);
+    PCK(cudaMemcpyAsync(p->h_level_off.data(), p->level_off.p, ((size_t)p->nlevels + 1) * 4, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    cleanup2();
+#undef PCK
+#undef PRC
+    p->norder = p->nlevels ? p->h_level_off[p->nlevels] : 0;
+    // tail = suffix of levels that are all at most TAIL_WIDTH wide
+    int tl = p->nlevels;
+    while (tl > 0 && p->h_level_off[tl] - p->h_level_off[tl - 1] <= TAIL_WIDTH) --tl;
+    if (tl < 1) tl = 1;                 // level 0 has nothing to add and is never swept
+    if (tl > p->nlevels) tl = p->nlevels;
+    p->tail_level = tl;
+    if ((rc = p->tailmask.ensure(n))) return rc;
+    if ((rc = p->done.ensure(n * 4))) return rc;
+    if ((rc = p->ticket.ensure(sizeof(int)))) return rc;
+    CK(cudaMemsetAsync(p->done.p, 0, n * 4, st));
+    CK(cudaMemsetAsync(p->tailmask.p, 0, n, st));
+    int tb = tl < p->nlevels ? p->h_level_off[tl] : p->norder, te = p->norder;
+    if (te > tb) {
+        k_tailmask<<<ceil_div(te - tb, 256), 256, 0, st>>>(p->order.as<int32_t>(), tb, te, p->ncol, tl,
+                                                           p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
+                                                           p->tailmask.as<uint8_t>());
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));
+    return GR2M_OK;
+}
+
+static int plan_create_common(const int16_t *flowdir, bool on_device, int nrow, int ncol, int flags, wfa_plan **out)
+{
+    REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    REQUIRE(flowdir != nullptr, "flowdir is NULL");
+    REQUIRE(nrow > 0 && ncol > 0, "nrow and ncol must be positive");
+    REQUIRE((long long)nrow * ncol < 0x7fffffffll, "grid too large for 32-bit cell ids");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(gr2m_current_device()));
+    wfa_plan *p = new (std::nothrow) wfa_plan();
+    if (!p) { gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
+    p->device = gr2m_current_device();
+    p->nrow = nrow; p->ncol = ncol; p->ncell = (long long)nrow * ncol; p->flags = flags;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e != cudaSuccess) {
+        gr2m_set_error("wfa_plan_create: %s", cudaGetErrorString(e));
+        plan_free(p);
+        return GR2M_ERR_CUDA;
+    }
+    p->stream = p->own_stream;
+    DevBuf dir;
+    const int16_t *dir_dev = flowdir;
+    if (!on_device) {
+        rc = dir.ensure(p->ncell * sizeof(int16_t));
+        if (!rc) {
+            e = cudaMemcpyAsync(dir.p, flowdir, p->ncell * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream);
+            if (e != cudaSuccess) { gr2m_set_error("wfa_plan_create: %s", cudaGetErrorString(e)); rc = GR2M_ERR_CUDA; }
+        }
+        dir_dev = dir.as<int16_t>();
+    }
+    if (!rc) rc = plan_build(p, dir_dev);
+    dir.release();
+    if (rc) { plan_free(p); return rc; }
+    *out = p;
+    return GR2M_OK;
+}
+
+extern "C" int wfa_plan_create(const int16_t *flowdir, int nrow, int ncol, int flags, wfa_plan **out)
+{
+    return plan_create_common(flowdir, false, nrow, ncol, flags, out);
+}
+
+extern "C" int wfa_plan_create_dev(const int16_t *flowdir_dev, int nrow, int ncol, int flags, wfa_plan **out)
+{
+    return plan_create_common(flowdir_dev, true, nrow, ncol, flags, out);
+}
+
+extern "C" int wfa_plan_destroy(wfa_plan *p)
+{
+    plan_free(p);
+    return GR2M_OK;
+}
+
+extern "C" int wfa_plan_set_stream(wfa_plan *p, void *cuda_stream)
+{
+    REQUIRE(p != nullptr, "plan is NULL");
+    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    return GR2M_OK;
+}
+
+extern "C" int wfa_plan_info(const wfa_plan *p, int *nlevels, int *norder, int64_t *ncell)
+{
+    REQUIRE(p != nullptr, "plan is NULL");
+    if (nlevels) *nlevels = p->nlevels;
+    if (norder) *norder = p->norder;
+    if (ncell) *ncell = p->ncell;
+    return GR2M_OK;
+}
+
+extern "C" int wfa_plan_export(const wfa_plan *pc, int32_t *receiver, uint8_t *inmask, int32_t *indeg, int32_t *level,
+                               int32_t *order, int32_t *level_off, uint8_t *contam)
+{
+    REQUIRE(pc != nullptr, "plan is NULL");
+    wfa_plan *p = const_cast<wfa_plan *>(pc);
+    CK(cudaSetDevice(p->device));
+    const long long n = p->ncell;
+    if (receiver) CK(cudaMemcpy(receiver, p->receiver.p, n * 4, cudaMemcpyDeviceToHost));
+    if (inmask) CK(cudaMemcpy(inmask, p->inmask.p, n, cudaMemcpyDeviceToHost));
+    if (indeg) CK(cudaMemcpy(indeg, p->indeg.p, n * 4, cudaMemcpyDeviceToHost));
+    if (level) CK(cudaMemcpy(level, p->level.p, n * 4, cudaMemcpyDeviceToHost));
+    if (order && p->norder) CK(cudaMemcpy(order, p->order.p, (size_t)p->norder * 4, cudaMemcpyDeviceToHost));
+    if (level_off) memcpy(level_off, p->h_level_off.data(), ((size_t)p->nlevels + 1) * 4);
+    if (contam) CK(cudaMemcpy(contam, p->contam.p, n, cudaMemcpyDeviceToHost));
+    return GR2M_OK;
+}
+
+extern "C" int wfa_plan_last_kernel_ms(wfa_plan *p, float *ms)
+{
+    REQUIRE(p && ms, "NULL argument");
+    REQUIRE(p->timed, "no timed call yet");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->ev1));
+    CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return GR2M_OK;
+}
+
+template <typename T, int G>
+static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
+{
+    cudaStream_t st = p->stream;
+    const int32_t *order = p->order.as<int32_t>();
+    const uint8_t *inmask = p->inmask.as<uint8_t>();
+    const std::vector<int32_t> &off = p->h_level_off;
+    const int gpb = 256 / G;   // cell groups per 256-thread block
+    // level 0 has no upstream cells: nothing to add
+    for (int l = 1; l < p->tail_level; ++l) {
+        int b = off[l], e = off[l + 1];
+        k_accum_level<T, G><<<ceil_div(e - b, gpb), 256, 0, st>>>(order, b, e, p->ncol, inmask, A, ld, nmonth);
+    }
+    CK(cudaGetLastError());
+    const int l0 = p->tail_level;
+    if (l0 < p->nlevels) {
+        if (flags & WFA_LEVEL_SYNC) {
+            k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, inmask, A,
+                                                   ld, nmonth);
+        } else {
+            int b = off[l0], e = p->norder;
+            p->epoch += 1;
+            CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
+            int groups = ceil_div(e - b, 4);
+            int blocks = std::min(ceil_div(groups, gpb), 148 * 4);
+            k_accum_dataflow<T, G><<<blocks, 256, 0, st>>>(order, b, e, p->ncol, inmask, p->tailmask.as<uint8_t>(), A, ld,
+                                                           nmonth, p->done.as<unsigned>(), p->epoch, p->ticket.as<int>());
+        }
+        CK(cudaGetLastError());
+    }
+    return GR2M_OK;
+}
+
+template <typename T>
+static int sweep(wfa_plan *p, int nmonth, int ld, T *A, int flags)
+{
+    if (nmonth >= 32) return sweep_g<T, 32>(p, nmonth, ld, A, flags);
+    if (nmonth >= 16) return sweep_g<T, 16>(p, nmonth, ld, A, flags);
+    if (nmonth >= 8) return sweep_g<T, 8>(p, nmonth, ld, A, flags);
+    return sweep_g<T, 4>(p, nmonth, ld, A, flags);
+}
+
+extern "C" int wfa_accumulate_dev(wfa_plan *p, int nmonth, int ld, void *WA_dev, int flags)
+{
+    REQUIRE(p && WA_dev, "NULL plan or buffer");
+    REQUIRE(nmonth > 0 && ld >= nmonth, "need 0 < nmonth <= ld");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->ev0, p->stream));
+    int rc = (flags & WFA_F32) ? sweep<float>(p, nmonth, ld, (float *)WA_dev, flags)
+                               : sweep<double>(p, nmonth, ld, (double *)WA_dev, flags);
+    if (rc) return rc;
+    CK(cudaEventRecord(p->ev1, p->stream));
+    p->timed = true;
+    return GR2M_OK;
+}
+
+extern "C" int wfa_mask_dev(wfa_plan *p, int nmonth, int ld, void *WA_dev, int flags)
+{
+    REQUIRE(p && WA_dev, "NULL plan or buffer");
+    REQUIRE(nmonth > 0 && ld >= nmonth, "need 0 < nmonth <= ld");
+    CK(cudaSetDevice(p->device));
+    const int use_contam = (flags & WFA_NO_CONTAMINATION) ? 0 : 1;
+    long long total = p->ncell * nmonth;
+    if (flags & WFA_F32)
+        k_mask<float><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
+                                                                  use_contam, p->ncell, (float *)WA_dev, ld, nmonth);
+    else
+        k_mask<double><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
+                                                                   use_contam, p->ncell, (double *)WA_dev, ld, nmonth);
+    CK(cudaGetLastError());
+    return GR2M_OK;
+}
+
+extern "C" int wfa_accumulate(wfa_plan *p, int nmonth, const double *W, int flags, double *A)
+{
+    REQUIRE(p && W && A, "NULL argument");
+    REQUIRE(nmonth > 0, "nmonth must be positive");
+    CK(cudaSetDevice(p->device));
+    const long long n = p->ncell;
+    const int ld = ceil_div(nmonth, 4) * 4;
+    const size_t esz = (flags & WFA_F32) ? 4 : 8;
+    int rc;
+    if ((rc = p->work.ensure((size_t)n * nmonth * 8))) return rc;
+    if ((rc = p->work2.ensure((size_t)n * ld * esz))) return rc;
+    cudaStream_t st = p->stream;
+    CK(cudaMemcpyAsync(p->work.p, W, (size_t)n * nmonth * 8, cudaMemcpyHostToDevice, st));
+    dim3 grid(ceil_div(n, 32), ceil_div(ld, 32)), blk(32, 8);
+    if (flags & WFA_F32) k_planes_to_cells<float><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<float>());
+    else k_planes_to_cells<double><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<double>());
+    CK(cudaGetLastError());
+    if ((rc = wfa_accumulate_dev(p, nmonth, ld, p->work2.p, flags))) return rc;
+    if ((rc = wfa_mask_dev(p, nmonth, ld, p->work2.p, flags))) return rc;
+    if (flags & WFA_F32) k_cells_to_planes<float><<<grid, blk, 0, st>>>(p->work2.as<float>(), n, nmonth, ld, p->work.as<double>());
+    else k_cells_to_planes<double><<<grid, blk, 0, st>>>(p->work2.as<double>(), n, nmonth, ld, p->work.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(A, p->work.p, (size_t)n * nmonth * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GR2M_OK;
+}
+
+extern "C" int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, const int32_t *src_cell,
+                         const int32_t *poly_off, const int32_t *poly_cells, int flags, double *QR)
+{
+    REQUIRE(p && QS && src_cell && poly_off && poly_cells && QR, "NULL argument");
+    REQUIRE(ntime > 0 && nsub > 0, "ntime and nsub must be positive");
+    const long long n = p->ncell;
+    for (int s = 0; s < nsub; ++s) {
+        REQUIRE(src_cell[s] >= 0 && src_cell[s] < n, "src_cell out of range (point on surface outside the DEM)");
+        REQUIRE(poly_off[s + 1] >= poly_off[s], "poly_off must be non-decreasing");
+    }
+    REQUIRE(poly_off[0] == 0, "poly_off[0] must be 0");
+    const int npc = poly_off[nsub];
+    for (int q = 0; q < npc; ++q) REQUIRE(poly_cells[q] >= 0 && poly_cells[q] < n, "poly_cells out of range");
+    CK(cudaSetDevice(p->device));
+    // duplicates: the last assignment wins, as R's `[<-` (Routing:109-113)
+    std::vector<int32_t> src(src_cell, src_cell + nsub);
+    {
+        std::vector<int> idx(nsub);
+        for (int s = 0; s < nsub; ++s) idx[s] = s;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return src_cell[a] < src_cell[b]; });
+        for (int i = 0; i + 1 < nsub; ++i)
+            if (src_cell[idx[i]] == src_cell[idx[i + 1]]) src[idx[i]] = -1;
+    }
+    const int ld = ceil_div(ntime, 4) * 4;
+    const size_t esz = (flags & WFA_F32) ? 4 : 8;
+    int rc;
+    if ((rc = p->work2.ensure((size_t)n * ld * esz))) return rc;
+    if ((rc = p->qs.ensure((size_t)nsub * ntime * 8))) return rc;
+    if ((rc = p->qr.ensure((size_t)nsub * ntime * 8))) return rc;
+    if ((rc = p->src.ensure((size_t)nsub * 4))) return rc;
+    if ((rc = p->poff.ensure(((size_t)nsub + 1) * 4))) return rc;
+    if ((rc = p->pcells.ensure(std::max<size_t>(4, (size_t)npc * 4)))) return rc;
+    cudaStream_t st = p->stream;
+    CK(cudaMemsetAsync(p->work2.p, 0, (size_t)n * ld * esz, st));
+    CK(cudaMemcpyAsync(p->qs.p, QS, (size_t)nsub * ntime * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->src.p, src.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->poff.p, poly_off, ((size_t)nsub + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (npc) CK(cudaMemcpyAsync(p->pcells.p, poly_cells, (size_t)npc * 4, cudaMemcpyHostToDevice, st));
+    const int nb = ceil_div((long long)nsub * ntime, 256);
+    const int use_contam = (flags & WFA_NO_CONTAMINATION) ? 0 : 1;
+    dim3 pg(nsub, ceil_div(ntime, 32));
+    if (flags & WFA_F32) {
+        k_scatter<float><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, p->work2.as<float>(), ld);
+        CK(cudaGetLastError());
+        if ((rc = wfa_accumulate_dev(p, ntime, ld, p->work2.p, flags))) return rc;
+        k_polygon_max<float><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+                                                 p->contam.as<uint8_t>(), use_contam, p->work2.as<float>(), ld, ntime,
+                                                 p->qr.as<double>());
+    } else {
+        k_scatter<double><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, p->work2.as<double>(), ld);
+        CK(cudaGetLastError());
+        if ((rc = wfa_accumulate_dev(p, ntime, ld, p->work2.p, flags))) return rc;
+        k_polygon_max<double><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+                                                  p->contam.as<uint8_t>(), use_contam, p->work2.as<double>(), ld, ntime,
+                                                  p->qr.as<double>());
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(QR, p->qr.p, (size_t)nsub * ntime * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GR2M_OK;
+}

@@ -1,0 +1,198 @@
+"""GPU parity: recursion + objective through the C ABI vs the CPU oracle (run with -m gpu on a B200).
+
+Tolerance (north_star: <= 1e-10 relative, FP64): |gpu - ref| <= 1e-10 * max(|ref|, 1) in the
+output's unit (mm or m3/s); the forcing correction round(f*x,1) must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+from gr2msemidistr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0), initial=0.0))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import __graft_entry__ as g
+    g.build()
+    from gr2msemidistr_b200 import capi as m
+    assert m.device_count() >= 1, "gpu tests need a CUDA device"
+    m.set_device(0)
+    return m
+
+
+def test_device_math_building_blocks(capi, oracle, rng):
+    # R round(x,1): fast path and exact path bit-identical to the oracle, incl. exact decimal ties
+    x = np.concatenate([rng.uniform(0, 4000, 200000), 1.186 * (rng.integers(0, 40000, 200000) / 10.0),
+                        rng.integers(0, 80000, 100000) / 20.0, [0.0, 0.05, 0.15, 0.25, 0.35, 29.65, 1e-9, 3839.95, -0.15, -7.25]])
+    want = oracle.r_round(x, 1)
+    assert np.array_equal(capi.debug_math(0, x), want)
+    assert np.array_equal(capi.debug_math(1, x), want)
+    for d in (2, 3):
+        v = np.concatenate([rng.uniform(-2, 5000, 100000), rng.integers(0, 10 ** 6, 50000) / 2000.0])
+        assert np.array_equal(capi.debug_math(5, v, np.full(v.size, float(d))), oracle.r_round(v, d))
+    # exp on [0, 26], division, reciprocal cube root on [1, 2]: a few ulp
+    e = rng.uniform(0, 26, 200000)
+    assert np.max(np.abs(capi.debug_math(2, e) / np.exp(e) - 1)) < 4e-16
+    n, dd = rng.uniform(0, 5000, 200000), rng.uniform(2, 4e11, 200000)
+    assert np.max(np.abs(capi.debug_math(3, n, dd) / (n / dd) - 1)) < 3e-16
+    c = rng.uniform(1, 2, 200000)
+    assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 4e-16
+
+
+@pytest.mark.parametrize("flags", [0, 16, 1, 17])
+def test_run_c1_shape_matches_oracle(capi, oracle, flags):
+    # config C1 shape: 13 subbasins x 432 months x 1 set, the documented parameter set
+    P, E, area, nd = synth.forcing(13, 432)
+    region = np.zeros(13, np.int32)
+    par = np.array(synth.SET0)
+    ref = oracle.run(P, E, area, nd, region, 1, par, flags=flags & 1)
+    with capi.Basin(P, E, area, nd, region, 1) as b:
+        got = b.run(par, flags=flags)
+    assert np.array_equal(got["PR"], ref["PR"])
+    for k in ("AE", "SM", "RU", "QS", "S_end", "R_end"):
+        assert relerr(got[k], ref[k]) <= TOL, k
+
+
+def test_run_multi_region_ragged_and_inistate(capi, oracle, rng):
+    # 3 regions, ncell not a multiple of 32, ntime not a multiple of the 16-month stage
+    ncell, ntime, nreg = 77, 61, 3
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=5)
+    region = rng.integers(0, nreg, ncell).astype(np.int32)
+    par = synth.param_sets(4, nreg, seed=9)[3]
+    ref = oracle.run(P, E, area, nd, region, nreg, par)
+    got = capi.run_once(P, E, area, nd, region, nreg, par)
+    assert np.array_equal(got["PR"], ref["PR"])
+    for k in ("AE", "SM", "RU", "QS", "S_end", "R_end"):
+        assert relerr(got[k], ref[k]) <= TOL, k
+    # EndState -> IniState hand-off (Run:151-179): two half runs equal the long run
+    h = 30
+    a = capi.run_once(P[:, :h], E[:, :h], area, nd[:h], region, nreg, par)
+    b = capi.run_once(P[:, h:], E[:, h:], area, nd[h:], region, nreg, par, S0=a["S_end"], R0=a["R_end"])
+    assert relerr(np.concatenate([a["QS"], b["QS"]], axis=1), ref["QS"]) <= TOL
+    assert relerr(b["S_end"], ref["S_end"]) <= TOL and relerr(b["R_end"], ref["R_end"]) <= TOL
+    # single month (Update mode, Run:138-142 needs a dummy month in airGR; not here)
+    one = capi.run_once(P[:, :1], E[:, :1], area, nd[:1], region, nreg, par)
+    assert relerr(one["QS"], ref["QS"][:, :1]) <= TOL
+
+
+def test_run_c3_shape(capi, oracle):
+    # config C3: 3 600 subbasins x 480 months, 14 regional parameter sets
+    ncell, ntime, nreg = 3600, 480, 14
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=3)
+    region = (np.arange(ncell) * 7 % nreg).astype(np.int32)
+    par = synth.param_sets(2, nreg, seed=4)[1]
+    ref = oracle.run(P, E, area, nd, region, nreg, par, nthreads=8)
+    with capi.Basin(P, E, area, nd, region, nreg) as b:
+        got = b.run(par)
+    assert np.array_equal(got["PR"], ref["PR"])
+    for k in ("AE", "SM", "RU", "QS"):
+        assert relerr(got[k], ref[k]) <= TOL, k
+
+
+def test_extreme_parameters_and_forcing(capi, oracle):
+    # bounds of the calibration box, X1/X2 below the airGR floor, P/X1 > 13 clamp, zero forcing
+    P, E, area, nd = synth.forcing(40, 48, seed=11)
+    P[0] = 0.0; E[1] = 0.0; P[2] = 3000.0; P[3, ::2] = 0.0
+    region = np.zeros(40, np.int32)
+    for par in ([1.0, 0.01, 0.8, 0.8], [2000.0, 2.0, 1.2, 1.2], [0.001, 0.0, 1.0, 1.0], [10.976, 0.665, 1.186, 1.169]):
+        par = np.array(par)
+        ref = oracle.run(P, E, area, nd, region, 1, par)
+        got = capi.run_once(P, E, area, nd, region, 1, par)
+        assert np.array_equal(got["PR"], ref["PR"])
+        for k in ("AE", "SM", "RU", "QS"):
+            assert relerr(got[k], ref[k]) <= TOL, (k, par)
+
+
+def _check_objective(capi, oracle, P, E, area, nd, region, nreg, par, warmup, flags=0):
+    base = oracle.run(P, E, area, nd, region, nreg, par[0])
+    qobs = synth.qobs_from(oracle.outlet_optim(base["QS"]))
+    with capi.Basin(P, E, area, nd, region, nreg) as b:
+        unr = b.objective_batch(par, qobs, warmup, capi.OF_NSE, flags | capi.SINK_UNROUNDED, want_qt=True)
+        rnd = {w: b.objective_batch(par, qobs, warmup, w, flags, want_qt=True) for w in (0, 1, 2)}
+        one = b.objective_batch(par[1:2], qobs, warmup, capi.OF_KGE, flags)      # the OFUN drop-in call
+    ref_u = oracle.objective_batch(P, E, area, nd, region, nreg, par, qobs, warmup, flags=(flags & 1) | oracle.SINK_UNROUNDED, nthreads=8)
+    ref_r = oracle.objective_batch(P, E, area, nd, region, nreg, par, qobs, warmup, flags=flags & 1, nthreads=8)
+    # unrounded sink and raw criteria: strict tolerance
+    assert relerr(unr["qt"], ref_u["qt"]) <= TOL
+    ok = np.isfinite(ref_u["crit"])
+    assert np.array_equal(np.isfinite(unr["crit"]), ok)
+    assert relerr(unr["crit"][ok], ref_u["crit"][ok]) <= TOL
+    # rounded path (Optim:195, 210-212): identical except where a sum sits on a rounding tie
+    dq = np.abs(rnd[1]["qt"] - ref_r["qt"])
+    assert np.all(dq <= 0.01 + 1e-9) and np.mean(dq > 1e-9) < 1e-4
+    for w in (0, 1, 2):
+        d = np.abs(rnd[w]["of"] - ref_r["of"][:, w])
+        okw = np.isfinite(ref_r["of"][:, w])
+        assert np.all(d[okw] <= 1e-3 + 1e-9) and np.mean(d[okw] > 1e-9) <= 0.01
+    assert abs(one["of"][0] - rnd[0]["of"][1]) == 0.0
+
+
+def test_objective_c2_shape(capi, oracle):
+    # config C2: 13 subbasins x 264 months (WarmUp 36) x many candidate sets (2 000 here; the oracle is serial)
+    P, E, area, nd = synth.forcing(13, 264)
+    _check_objective(capi, oracle, P, E, area, nd, np.zeros(13, np.int32), 1, synth.param_sets(2000), 36)
+
+
+def test_objective_multi_tile_multi_region(capi, oracle, rng):
+    # several cell tiles and cell splits, ragged sizes, 2 regions, sets not a multiple of 8
+    ncell, ntime, nreg = 333, 75, 2
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=21)
+    region = rng.integers(0, nreg, ncell).astype(np.int32)
+    _check_objective(capi, oracle, P, E, area, nd, region, nreg, synth.param_sets(61, nreg, seed=22), 12)
+    _check_objective(capi, oracle, P, E, area, nd, region, nreg, synth.param_sets(9, nreg, seed=23), 0, flags=capi.MATH_LITERAL)
+    _check_objective(capi, oracle, P, E, area, nd, region, nreg, synth.param_sets(9, nreg, seed=24), 0, flags=capi.PERC_F32_EXPONENT)
+
+
+def test_objective_single_subbasin_branch(capi, oracle):
+    # nsub == 1: sink is the unrounded QS (Optim:187-188)
+    P, E, area, nd = synth.forcing(1, 120, seed=31)
+    par = synth.param_sets(17)
+    base = oracle.run(P, E, area, nd, np.zeros(1, np.int32), 1, par[0])
+    qobs = synth.qobs_from(base["QS"][0])
+    with capi.Basin(P, E, area, nd, np.zeros(1, np.int32), 1) as b:
+        got = b.objective_batch(par, qobs, 12, capi.OF_RMSE, want_qt=True)
+    ref = oracle.objective_batch(P, E, area, nd, np.zeros(1, np.int32), 1, par, qobs, 12)
+    assert relerr(got["qt"], ref["qt"]) <= TOL
+    assert relerr(got["crit"], ref["crit"]) <= TOL
+
+
+def test_sharding_by_parameter_set_is_bit_identical(capi):
+    # multi-GPU design: each rank evaluates a slice of the sets against replicated
+    # forcing; a slice must give exactly the bits the full batch gives
+    P, E, area, nd = synth.forcing(200, 96, seed=41)
+    region = np.zeros(200, np.int32)
+    par = synth.param_sets(96)
+    qobs = synth.qobs_from(np.full(96, 50.0))
+    with capi.Basin(P, E, area, nd, region, 1) as b:
+        full = b.objective_batch(par, qobs, 12, capi.OF_NSE, want_qt=True)
+        parts = [b.objective_batch(par[i:i + 24], qobs, 12, capi.OF_NSE, want_qt=True) for i in range(0, 96, 24)]
+    assert np.array_equal(np.concatenate([p["qt"] for p in parts]), full["qt"])
+    assert np.array_equal(np.concatenate([p["of"] for p in parts]), full["of"], equal_nan=True)
+
+
+def test_large_sweep_properties(capi):
+    # BASELINE-scale slice where the oracle is too slow: size-independent properties.
+    # (i) the result for a set does not depend on which other sets share the batch (checked above);
+    # (ii) permuting the subbasins permutes nothing in the outlet sum beyond re-association (<= 1e-12);
+    # (iii) duplicating every subbasin with half the area leaves the outlet series unchanged.
+    ncell, ntime, nsets = 4096, 480, 256
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=51)
+    region = np.zeros(ncell, np.int32)
+    par = synth.param_sets(nsets)
+    with capi.Basin(P, E, area, nd, region, 1) as b:
+        q0 = b.objective_batch(par, None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
+    perm = np.random.default_rng(1).permutation(ncell)
+    with capi.Basin(P[perm], E[perm], area[perm], nd, region, 1) as b:
+        q1 = b.objective_batch(par, None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
+    assert relerr(q1, q0) <= 1e-12
+    P2, E2, a2 = np.repeat(P, 2, 0), np.repeat(E, 2, 0), np.repeat(area / 2, 2)
+    with capi.Basin(P2, E2, a2, nd, np.zeros(2 * ncell, np.int32), 1) as b:
+        q2 = b.objective_batch(par, None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
+    assert relerr(q2, q0) <= 1e-12
+    assert np.all(np.isfinite(q0)) and np.all(q0 >= 0)

@@ -1,0 +1,159 @@
+"""GPU parity: D8 plan (bit-exact integers) and Weighted Flow Accumulation vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from gr2msemidistr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+N = -32768
+PLAN_KEYS = ("receiver", "inmask", "indeg", "level", "order", "level_off", "contam")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import __graft_entry__ as g
+    g.build()
+    from gr2msemidistr_b200 import capi as m
+    assert m.device_count() >= 1, "gpu tests need a CUDA device"
+    m.set_device(0)
+    return m
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0), initial=0.0))
+
+
+@pytest.mark.parametrize("shape", [(5, 5), (64, 96), (251, 429), (700, 900)])
+def test_plan_bit_exact(capi, oracle, shape):
+    d = synth.d8_grid(*shape, seed=shape[0]).numpy()
+    ref = oracle.d8_plan(d)
+    with capi.Plan(d) as p:
+        got = p.export()
+    assert got["nlevels"] == ref["nlevels"]
+    for k in PLAN_KEYS:
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_plan_edge_cases(capi, oracle, rng):
+    # all nodata; a single valid cell; random directions with cycles (cycle cells and everything
+    # behind them are never evaluated, as in TauDEM); one row; one column
+    cases = [np.full((4, 6), N, np.int16), np.array([[N, N, N], [N, 1, N], [N, N, N]], np.int16),
+             rng.integers(0, 10, (40, 50)).astype(np.int16), rng.integers(1, 9, (1, 64)).astype(np.int16),
+             rng.integers(1, 9, (64, 1)).astype(np.int16)]
+    for d in cases:
+        ref = oracle.d8_plan(d)
+        with capi.Plan(d) as p:
+            got = p.export()
+            for k in PLAN_KEYS:
+                assert np.array_equal(got[k], ref[k]), k
+            W = rng.uniform(0, 10, (3,) + d.shape)
+            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_LEVEL_SYNC):
+                A = p.accumulate(W, fl)
+                Ar = np.stack([oracle.aread8(d, W[m], contcheck=not (fl & capi.WFA_NO_CONTAMINATION)) for m in range(3)])
+                assert np.array_equal(np.isnan(A), np.isnan(Ar))
+                assert relerr(np.nan_to_num(A), np.nan_to_num(Ar)) <= 1e-10
+
+
+@pytest.mark.parametrize("nmonth", [1, 5, 12, 33, 70])
+def test_accumulate_dense_matches_oracle(capi, oracle, rng, nmonth):
+    d = synth.d8_grid(150, 210, seed=7).numpy()
+    W = rng.uniform(0, 100, (nmonth, 150, 210))
+    with capi.Plan(d) as p:
+        for fl in (0, capi.WFA_LEVEL_SYNC, capi.WFA_NO_CONTAMINATION):
+            A = p.accumulate(W, fl)
+            cc = not (fl & capi.WFA_NO_CONTAMINATION)
+            for m in {0, nmonth // 2, nmonth - 1}:
+                Ar = oracle.aread8(d, W[m], contcheck=cc)
+                assert np.array_equal(np.isnan(A[m]), np.isnan(Ar))
+                # same k-ordered FP64 additions as the oracle => identical bits
+                assert np.array_equal(np.nan_to_num(A[m]), np.nan_to_num(Ar))
+        # TauDEM-faithful float32 mode is bit-exact against the oracle's float32 mode
+        A32 = p.accumulate(W, capi.WFA_F32)
+        for m in {0, nmonth - 1}:
+            Ar = oracle.aread8(d, W[m], f32=True, contcheck=True)
+            assert np.array_equal(np.nan_to_num(A32[m], nan=-1), np.nan_to_num(Ar, nan=-1))
+
+
+def test_dataflow_tail_on_long_thin_network(capi, oracle, rng):
+    # one long meandering channel: thousands of levels with 1-2 cells each (the routing tail)
+    nrow, ncol = 64, 257
+    d = np.full((nrow, ncol), N, np.int16)
+    for r in range(1, nrow - 1, 2):
+        if (r // 2) % 2 == 0:
+            d[r, 1:ncol - 1] = 1; d[r, ncol - 2] = 7; d[r + 1, ncol - 2] = 7
+        else:
+            d[r, 1:ncol - 1] = 5; d[r, 1] = 7; d[r + 1, 1] = 7
+    d[nrow - 2:, :] = N
+    ref = oracle.d8_plan(d)
+    assert ref["nlevels"] > 5000
+    W = rng.uniform(0, 10, (8, nrow, ncol))
+    with capi.Plan(d) as p:
+        got = p.export()
+        for k in PLAN_KEYS:
+            assert np.array_equal(got[k], ref[k]), k
+        for fl in (capi.WFA_NO_CONTAMINATION, capi.WFA_NO_CONTAMINATION | capi.WFA_LEVEL_SYNC):
+            A = p.accumulate(W, fl)
+            for m in (0, 7):
+                Ar = oracle.aread8(d, W[m], contcheck=False)
+                assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(Ar, nan=-1))
+
+
+def test_route_matches_oracle_c1_shape(capi, oracle, rng):
+    # config C1 shape: 251 x 429 grid, 13 subbasins, 432 months
+    nrow, ncol = 251, 429
+    d = synth.d8_grid(nrow, ncol, seed=13).numpy()
+    src, off, cells = synth.block_polygons(nrow, ncol, 3, 5, margin=3)
+    src, off = src[:13], off[:14]
+    cells = cells[:off[-1]]
+    QS = rng.uniform(0, 400, (13, 432))
+    ref = oracle.route(d, QS, src, off, cells, nthreads=8)
+    ref32 = oracle.route(d, QS, src, off, cells, f32=True, nthreads=8)
+    with capi.Plan(d) as p:
+        QR = p.route(QS, src, off, cells)
+        QR_ls = p.route(QS, src, off, cells, capi.WFA_LEVEL_SYNC)
+        QR32 = p.route(QS, src, off, cells, capi.WFA_F32)
+        QRnc = p.route(QS, src, off, cells, capi.WFA_NO_CONTAMINATION)
+    assert np.array_equal(QR, ref) and np.array_equal(QR_ls, ref)
+    assert np.array_equal(QR32, ref32)
+    assert np.array_equal(QRnc, oracle.route(d, QS, src, off, cells, contcheck=False, nthreads=8))
+
+
+def test_route_edge_cases(capi, oracle, rng):
+    nrow, ncol = 96, 128
+    d = synth.d8_grid(nrow, ncol).numpy()
+    src, off, cells = synth.block_polygons(nrow, ncol, 3, 4, margin=2)
+    QS = rng.uniform(0, 300, (12, 7))
+    with capi.Plan(d) as p:
+        # duplicate source cells: the last assignment wins (R `[<-`)
+        src2 = src.copy(); src2[1] = src2[0]; src2[5] = src2[0]
+        assert np.array_equal(p.route(QS, src2, off, cells, capi.WFA_NO_CONTAMINATION),
+                              oracle.route(d, QS, src2, off, cells, contcheck=False))
+        # an empty polygon gives -Inf (R max() of nothing), a single month works (Update mode)
+        off2 = off.copy(); off2[4:] -= off2[4] - off2[3]
+        cells2 = np.concatenate([cells[:off[3]], cells[off[4]:]])
+        got = p.route(QS[:, :1], src, off2, cells2)
+        assert np.array_equal(got, oracle.route(d, QS[:, :1], src, off2, cells2))
+        assert got[3, 0] == -np.inf
+        # out-of-range cells are rejected, not read
+        bad = src.copy(); bad[0] = nrow * ncol
+        with pytest.raises(capi.GR2MError):
+            p.route(QS, bad, off, cells)
+
+
+def test_linearity_and_mass_conservation_large(capi, rng):
+    # BASELINE-scale property test (oracle-free): integer weights make sums exact, so
+    # route(3 W1 + 2 W2) == 3 route(W1) + 2 route(W2) bit for bit, and terminal cells hold the total
+    nrow, ncol, nm = 1500, 2000, 4
+    d = synth.d8_grid(nrow, ncol, seed=99).numpy()
+    W1 = rng.integers(0, 50, (nm, nrow, ncol)).astype(float)
+    W2 = rng.integers(0, 50, (nm, nrow, ncol)).astype(float)
+    with capi.Plan(d) as p:
+        pl = p.export()
+        fl = capi.WFA_NO_CONTAMINATION
+        A1, A2, A12 = p.accumulate(W1, fl), p.accumulate(W2, fl), p.accumulate(3 * W1 + 2 * W2, fl)
+    ok = ~np.isnan(A12)
+    assert np.array_equal(A12[ok], (3 * A1 + 2 * A2)[ok])
+    term = ((pl["receiver"] < 0) & (pl["level"] >= 0)).reshape(nrow, ncol)
+    valid = (pl["level"] >= 0).reshape(nrow, ncol)
+    for m in range(nm):
+        assert A1[m][term].sum() == W1[m][valid].sum()
