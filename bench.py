@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--months", type=int, default=480)
     ap.add_argument("--route-n", type=int, default=20_000, help="side of the synthetic D8 grid (0 = skip routing)")
     ap.add_argument("--route-batch", type=int, default=16, help="months per routing batch")
+    ap.add_argument("--route-flags", type=int, default=0, help="WFA_* flags for the routing sweep")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--literal", action="store_true", help="use the literal (IEEE division) kernel variant")
@@ -107,7 +108,7 @@ def cpu_port(a, nthreads, seconds):
     region = np.zeros(cells, np.int32)
     qobs = synth.qobs_from(np.full(a.months, 100.0))
     # calibrate the sample size on a tiny run, then size it for ~`seconds`
-    par = synth.param_sets(max(nthreads, 8))
+    par = synth.param_sets(4 * max(nthreads, 8))
     t0 = time.perf_counter()
     oracle.objective_batch(P, E, area, nd, region, 1, par, qobs, warmup=36, nthreads=nthreads, want_qt=False)
     dt = time.perf_counter() - t0
@@ -181,7 +182,7 @@ def bench_routing(a, capi, torch, rank, world, dist):
             m = min(ld, my_months - b * ld)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            plan.accumulate_dev(A.data_ptr(), m, ld)
+            plan.accumulate_dev(A.data_ptr(), m, ld, a.route_flags)
             e1.record()
             e1.synchronize()
             tot += e0.elapsed_time(e1)
@@ -246,7 +247,9 @@ def main():
     nloc = s1 - s0
     flags = capi.MATH_LITERAL if a.literal else 0
 
-    stream = torch.cuda.current_stream()
+    # a side stream: the legacy default stream's handle is 0, which the C ABI reads as "own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     basin = capi.Basin(P, E, area, nd, region, 1)
     basin.set_stream(stream.cuda_stream)
     par_d = torch.from_numpy(par).to(dev)

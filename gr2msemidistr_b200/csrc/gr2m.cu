@@ -74,7 +74,7 @@ constexpr int STAGE_DBL = TM * 64;
 
 // raw [ncell][ntime] (R column-major) -> tiled month-major F[tile][t][var][32]
 __global__ void k_tile_forcing(const double *__restrict__ P, const double *__restrict__ E, int ncell, int ntime,
-                               int ntime_pad, double *__restrict__ F)
+                               int ntime_pad, double *__restrict__ F, int *__restrict__ bad)
 {
     __shared__ double sp[32][33], se[32][33];
     int tile = blockIdx.x, t0 = blockIdx.y * 32;
@@ -82,8 +82,10 @@ __global__ void k_tile_forcing(const double *__restrict__ P, const double *__res
     for (int j = ly; j < 32; j += 8) {
         int c = tile * 32 + j, t = t0 + lx;
         bool ok = c < ncell && t < ntime;
-        sp[j][lx] = ok ? P[(size_t)c * ntime + t] : 0.0;
-        se[j][lx] = ok ? E[(size_t)c * ntime + t] : 0.0;
+        double pv = ok ? P[(size_t)c * ntime + t] : 0.0, ev = ok ? E[(size_t)c * ntime + t] : 0.0;
+        sp[j][lx] = pv;
+        se[j][lx] = ev;
+        if (!(fabs(pv) < 1e9 && fabs(ev) < 1e9)) *bad = 1;   // also catches NaN / Inf
     }
     __syncthreads();
     for (int j = ly; j < 32; j += 8) {
@@ -112,7 +114,8 @@ __global__ void k_transpose(const double *__restrict__ in, int rows, int cols, i
     }
 }
 
-__device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int nreg, int reg, double area)
+__device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int nreg, int reg, double area,
+                                            bool forcing_ok)
 {
     CellPar p;
     p.X1 = fmax(par[reg], 0.01);             // RunModel_GR2M.R floors X1, X2 at 1e-2
@@ -120,7 +123,10 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.fp = par[2 * nreg + reg];
     p.fe = par[3 * nreg + reg];
     p.iX1 = 1.0 / p.X1;
+    p.i2X1 = 2.0 / p.X1;
     p.area = area;
+    // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
+    p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? 0.499 : -1.0;
     return p;
 }
 
@@ -154,7 +160,7 @@ struct CalibArgs {
     const double *F, *area, *params, *tconv;   // tconv: conv[t] (fast) or den[t] (literal)
     const int *region;
     double *partial;                           // [csplit][nsets][ntime]
-    int ncell, ntiles, ntime, ntime_pad, nreg, nsets, nsg, tiles_per_split, f32exp;
+    int ncell, ntiles, ntime, ntime_pad, nreg, nsets, nsg, tiles_per_split, f32exp, forcing_ok;
 };
 
 // Calibration-mode recursion: every (cell, set) is simulated for all months; only the outlet sums
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(SPB * 32, 3) k_gr2m_calib(CalibArgs a)
     for (int tile = tile0; tile < tile1; ++tile) {
         const int cell = tile * 32 + lane;
         const bool cell_ok = cell < a.ncell;
-        CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0);
+        CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0, a.forcing_ok);
         double S = 0.3 * p.X1, R = 0.5 * p.X2;   // airGR default IniResLevels (Optim never passes IniState)
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
             if (tid == 0 && g + NST - 1 < total) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(SPB * 32, 3) k_gr2m_calib(CalibArgs a)
             mbar_wait(&full[g % NST], (g / NST) & 1);
             if (set_ok) {
                 const double *sp = stage + (g % NST) * STAGE_DBL;
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < TM / 8; ++h) {
                     double v[8];
 #pragma unroll
@@ -244,7 +250,7 @@ struct SimArgs {
     const int *region;
     double *out;        // [5][ntime][ncell_pad] month-major: PR, AE, SM, RU, QS
     double *S_end, *R_end;
-    int ncell, ncell_pad, ntime, ntime_pad, nreg, f32exp;
+    int ncell, ncell_pad, ntime, ntime_pad, nreg, f32exp, forcing_ok;
 };
 
 // Simulation-mode recursion: one parameter vector, every series written (Run:223-229).
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(128) k_gr2m_sim(SimArgs a)
     if (cell >= a.ncell_pad) return;
     const bool ok = cell < a.ncell;
     const int tile = cell >> 5, lane = cell & 31;
-    CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0);
+    CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0, a.forcing_ok);
     double S = (a.S0 && ok) ? a.S0[cell] : 0.3 * p.X1;
     double R = (a.R0 && ok) ? a.R0[cell] : 0.5 * p.X2;
     const double *f = a.F + (size_t)tile * a.ntime_pad * 64 + lane;
@@ -367,11 +373,12 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
     if (i >= n) return;
     double r;
     switch (op) {
-        case 0: r = r_round1(x[i]); break;
+        case 0: r = r_round1(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
         case 1: r = r_round1_exact(x[i]); break;
         case 2: r = exp_tab(x[i], tab); break;
         case 3: r = div_fast(x[i], y[i]); break;
         case 4: r = rcbrt_fast(x[i]); break;
+        case 6: r = div_fast1(x[i], y[i]); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;
@@ -405,6 +412,7 @@ struct gr2m_basin {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    int forcing_ok = 0;   // every |P|, |E| < 1e9 and finite (checked on the device at upload)
     DevBuf F, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
     double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
     int qobs_n = 0;
@@ -454,7 +462,7 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
     BCK(b->area.ensure(ncell * sizeof(double)));
     BCK(b->region.ensure(ncell * sizeof(int)));
     BCK(b->den.ensure(ntime * sizeof(double)));
-    BCK(b->conv.ensure(ntime * sizeof(double)));
+    BCK(b->conv.ensure(ntime * sizeof(double) + 16));   // + a device flag used while tiling
     DevBuf rawP, rawE;
     int r1 = rawP.ensure(nraw), r2 = rawE.ensure(nraw);
     if (r1 || r2) { rawP.release(); rawE.release(); basin_free(b); return r1 ? r1 : r2; }
@@ -471,9 +479,15 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
     step(cudaMemcpyAsync(b->conv.p, den + ntime, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     if (e == cudaSuccess) {
         dim3 grid(b->ntiles, ceil_div(b->ntime_pad, 32)), blk(32, 8);
+        int *bad = reinterpret_cast<int *>(b->conv.as<char>() + (size_t)ntime * sizeof(double));
+        step(cudaMemsetAsync(bad, 0, sizeof(int), b->stream));
         k_tile_forcing<<<grid, blk, 0, b->stream>>>(rawP.as<double>(), rawE.as<double>(), ncell, ntime, b->ntime_pad,
-                                                   b->F.as<double>());
+                                                   b->F.as<double>(), bad);
         step(cudaGetLastError());
+        int hbad = 1;
+        step(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        step(cudaStreamSynchronize(b->stream));
+        b->forcing_ok = hbad ? 0 : 1;
     }
     step(cudaStreamSynchronize(b->stream));
     free(den);
@@ -536,7 +550,7 @@ extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, c
     a.region = b->region.as<int>(); a.out = b->sim_out.as<double>();
     a.S_end = b->send.as<double>(); a.R_end = b->rend.as<double>();
     a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad;
-    a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
+    a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
     CK(cudaEventRecord(b->ev0, b->stream));
     int grid = ceil_div(b->ncell_pad, 128);
     if (flags & GR2M_MATH_LITERAL) k_gr2m_sim<false><<<grid, 128, 0, b->stream>>>(a);
@@ -621,6 +635,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.ncell = b->ncell; a.ntiles = b->ntiles; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad; a.nreg = b->nreg;
     a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
+    a.forcing_ok = b->forcing_ok;
     size_t smem = (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
     auto kern = fast ? k_gr2m_calib<true> : k_gr2m_calib<false>;

@@ -26,13 +26,35 @@ __constant__ double c_exp2_tab[32] = {
 
 #define GR2M_MAGIC 6755399441055744.0   /* 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51 */
 
+// 64-bit literals that do not fit an instruction immediate.  Kept in constant memory so DFMA/DMUL
+// read them as c[bank][offset] operands instead of re-materialising them with two MOVs per use
+// (the first build spent ~60 of its ~200 instructions per month on such moves).
+struct MathK {
+    double magic, nmagic, tenth, inv_ln2_32, nln2_32_hi, ln2_32_lo, c6, c5, c4, c3, two_ninths, third, tie_thr,
+        nf32_delta;
+};
+__constant__ MathK KC = {GR2M_MAGIC,
+                         -GR2M_MAGIC,
+                         0.1,
+                         0x1.71547652b82fep+5,    // 32 / ln 2
+                         -0x1.62e42ff000000p-6,   // -(ln2/32) high part (29 significant bits)
+                         0x1.718432a1b0e26p-40,   // -(ln2/32) low part
+                         0x1.6c16c16c16c17p-10,   // 1/720
+                         0x1.1111111111111p-7,    // 1/120
+                         0x1.5555555555555p-5,    // 1/24
+                         0x1.5555555555555p-3,    // 1/6
+                         0x1.c71c71c71c71cp-3,    // 2/9
+                         0x1.5555555555555p-2,    // 1/3
+                         0.499,
+                         -9.9341074625651041667e-9};   // -((double)(1.f/3.f) - 1/3)
+
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
 __device__ __forceinline__ double div10_rn(double n)
 {
-    double q = __dmul_rn(n, 0.1);
-    double r = __fma_rn(-q, 10.0, n);
-    return __fma_rn(r, 0.1, q);
+    double q = __dmul_rn(n, KC.tenth);
+    double r = __fma_rn(q, -10.0, n);
+    return __fma_rn(r, KC.tenth, q);
 }
 
 // R >= 4.0 algorithm verbatim: candidates floor/ceil(10x)/10, closer one wins in
@@ -50,13 +72,16 @@ __device__ __noinline__ double r_round1_exact(double x)
     return copysign(r, x);
 }
 
-// Same result, cheap common case: away from a decimal tie the winner is rint(10x)/10.
-__device__ __forceinline__ double r_round1(double x)
+// Same result, cheap common case: away from a decimal tie the winner is rint(10x)/10 (for either
+// sign).  Valid while |10x| < 2^51; `thr` is 0.499 when the caller has bounded |x| < 1e14 (forcing
+// checked at upload, factors at parameter load) and -1 otherwise, which sends every value down
+// the exact path.  NaN fails the comparison and takes the exact path too.
+__device__ __forceinline__ double r_round1(double x, double thr)
 {
     double x10 = __dmul_rn(x, 10.0);
-    double n = __dadd_rn(__dadd_rn(x10, GR2M_MAGIC), -GR2M_MAGIC);
+    double n = __dadd_rn(__dadd_rn(x10, KC.magic), KC.nmagic);
     double f = __dsub_rn(x10, n);
-    if (!(fabs(f) < 0.499 && x >= 0.0 && x10 < 1e15)) return r_round1_exact(x);
+    if (!(fabs(f) < thr)) return r_round1_exact(x);
     return div10_rn(n);
 }
 
@@ -82,15 +107,14 @@ __device__ double r_round_dig(double x, int dig)
 // exp(x) = 2^(k>>5) * 2^((k&31)/32) * (1 + r + ... + r^6/720); truncation 3.5e-18, total ~1 ulp.
 __device__ __forceinline__ double exp_tab(double x, const double *__restrict__ tab)
 {
-    double t = __fma_rn(x, 0x1.71547652b82fep+5, GR2M_MAGIC);
+    double t = __fma_rn(x, KC.inv_ln2_32, KC.magic);
     int ki = __double2loint(t);
-    double kd = __dadd_rn(t, -GR2M_MAGIC);
-    double r = __fma_rn(kd, -0x1.62e42ff000000p-6, x);
-    r = __fma_rn(kd, 0x1.718432a1b0e26p-40, r);
-    double p = 0x1.6c16c16c16c17p-10;
-    p = __fma_rn(p, r, 0x1.1111111111111p-7);
-    p = __fma_rn(p, r, 0x1.5555555555555p-5);
-    p = __fma_rn(p, r, 0x1.5555555555555p-3);
+    double kd = __dadd_rn(t, KC.nmagic);
+    double r = __fma_rn(kd, KC.nln2_32_hi, x);
+    r = __fma_rn(kd, KC.ln2_32_lo, r);
+    double p = __fma_rn(r, KC.c6, KC.c5);
+    p = __fma_rn(p, r, KC.c4);
+    p = __fma_rn(p, r, KC.c3);
     p = __fma_rn(p, r, 0.5);
     p = __fma_rn(p, r, 1.0);
     p = __fma_rn(p, r, 1.0);
@@ -119,6 +143,18 @@ __device__ __forceinline__ double div_fast(double n, double d)
     return __fma_rn(rem, r, q);
 }
 
+// one Newton step only: enough if the MUFU seed is good to ~2^-20 (error 2^-40 on r, squared away by
+// the quotient correction).  Measured against IEEE division in tests before it is used.
+__device__ __forceinline__ double div_fast1(double n, double d)
+{
+    double r = rcp_seed(d);
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    double q = __dmul_rn(n, r);
+    double rem = __fma_rn(-d, q, n);
+    return __fma_rn(rem, r, q);
+}
+
 // c^(-1/3) for c in [1, 2] (works for any normal c > 0): FP32 MUFU seed (~2^-21), one Halley step
 // y <- y + y e (1/3 + 2/9 e), e = 1 - c y^3   (cubic: residual ~ e^3)
 __device__ __forceinline__ double rcbrt_fast(double c)
@@ -131,13 +167,13 @@ __device__ __forceinline__ double rcbrt_fast(double c)
     double y = (double)y0;
     double y3 = __dmul_rn(__dmul_rn(y, y), y);
     double e = __fma_rn(-c, y3, 1.0);
-    double q = __fma_rn(e, 0x1.c71c71c71c71cp-3, 0x1.5555555555555p-2);
+    double q = __fma_rn(e, KC.two_ninths, KC.third);
     return __fma_rn(__dmul_rn(y, e), q, y);
 }
 
 // ---- the month step -----------------------------------------------------------------------------
 struct CellPar {
-    double X1, X2, iX1, fp, fe, area;
+    double X1, X2, iX1, i2X1, fp, fe, area, thr;   // i2X1 = 2/X1; thr: see r_round1
 };
 
 struct StepOut {
@@ -146,34 +182,40 @@ struct StepOut {
 
 #define GR2M_F32_EXP_DELTA 9.9341074625651041667e-9   /* (double)(1.f/3.f) - 1/3 */
 
+// min(x, 26) for the exp argument, decided on the high word by the integer ALU instead of a DSETP on the
+// FP64 pipe: for x >= 26 (or NaN, like fmin) the high word is >= that of 26.0, whose low word is 0;
+// negative x has a negative high word and passes through.
+__device__ __forceinline__ double clamp26(double x)
+{
+    return __double2hiint(x) >= 0x403A0000 ? 26.0 : x;
+}
+
 __device__ __forceinline__ StepOut step_fast(const CellPar &p, double Praw, double Eraw, double &S, double &R,
                                              bool f32exp, const double *__restrict__ tab)
 {
     StepOut o;
-    double Pc = r_round1(__dmul_rn(p.fp, Praw));
-    double Ec = r_round1(__dmul_rn(p.fe, Eraw));
-    // production store: S1 = (S + X1 T)/(1 + S/X1 T), T = tanh(w) = (a-1)/(a+1), a = exp(2w)
-    double w = fmin(Pc * p.iX1, 13.0);
-    double a = exp_tab(w + w, tab);
+    double Pc = r_round1(__dmul_rn(p.fp, Praw), p.thr);
+    double Ec = r_round1(__dmul_rn(p.fe, Eraw), p.thr);
+    // production store: S1 = (S + X1 T)/(1 + S/X1 T), T = tanh(w) = (a-1)/(a+1), a = exp(2w), w <= 13
+    double a = exp_tab(clamp26(Pc * p.i2X1), tab);
     double am1 = a - 1.0, ap1 = a + 1.0;
     double s = S * p.iX1;
-    double S1 = div_fast(__fma_rn(p.X1, am1, S * ap1), __fma_rn(s, am1, ap1));
+    double S1 = div_fast1(__fma_rn(p.X1, am1, S * ap1), __fma_rn(s, am1, ap1));
     double P1 = (Pc + S) - S1;
     // evaporation: S2 = S1 (1-T)/(1 + (1 - S1/X1) T) = 2 S1 / ((b+1) + (1 - S1/X1)(b-1)), b = exp(2w)
-    w = fmin(Ec * p.iX1, 13.0);
-    double b = exp_tab(w + w, tab);
+    double b = exp_tab(clamp26(Ec * p.i2X1), tab);
     double s1 = S1 * p.iX1;
-    double S2 = div_fast(S1 + S1, __fma_rn(1.0 - s1, b - 1.0, b + 1.0));
+    double S2 = div_fast1(S1 + S1, __fma_rn(1.0 - s1, b - 1.0, b + 1.0));
     o.AE = S1 - S2;
     // percolation: S = S2 / (1 + (S2/X1)^3)^(1/3)
     double sr = S2 * p.iX1;
     double c = __fma_rn(sr * sr, sr, 1.0);
     double y = rcbrt_fast(c);
-    if (f32exp) y = __fma_rn(-GR2M_F32_EXP_DELTA * (double)__logf(__double2float_rn(c)), y, y);
+    if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
     S = S2 * y;
     // routing store with exchange: R2 = X2 (R + P1 + P2), Q = R2^2/(R2 + 60)
     double R2 = p.X2 * (R + (P1 + (S2 - S)));
-    double Q = div_fast(R2 * R2, R2 + 60.0);
+    double Q = div_fast1(R2 * R2, R2 + 60.0);
     R = R2 - Q;
     o.Pc = Pc;
     o.Q = Q;

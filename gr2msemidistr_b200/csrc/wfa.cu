@@ -115,11 +115,12 @@ __global__ void __launch_bounds__(1024) k_peel_thin(int32_t *buf0, int32_t *buf1
 }
 
 __global__ void k_sort_keys(const int32_t *__restrict__ level, long long n, int nlevels, uint32_t *__restrict__ keys,
-                            int32_t *__restrict__ vals)
+                            int32_t *__restrict__ vals, uint8_t *__restrict__ contam)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int l = level[i];
+    if (l < 0) contam[i] = 0;   // never evaluated (nodata, on or behind a cycle): no contamination state
     keys[i] = l < 0 ? (uint32_t)nlevels : (uint32_t)l;
     vals[i] = (int32_t)i;
 }
@@ -456,7 +457,8 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PRC(vals.ensure(n * 4));
     PRC(p->order.ensure(n * 4));
     PRC(p->level_off.ensure(((size_t)p->nlevels + 2) * 4));
-    k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>());
+    k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>(),
+                                    p->contam.as<uint8_t>());
     PCK(cudaGetLastError());
     int bits = 1;
     while ((1ll << bits) <= p->nlevels) ++bits;

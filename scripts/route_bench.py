@@ -1,0 +1,33 @@
+"""Time the batched WFA sweep variants on a synthetic D8 grid (development aid, GPU only)."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as g
+from gr2msemidistr_b200 import capi, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=8000)
+ap.add_argument("--batches", default="16,32")
+ap.add_argument("--flags", default="0,4")
+a = ap.parse_args()
+g.build(); capi.set_device(0)
+dev = torch.device("cuda", 0)
+st = torch.cuda.Stream(device=dev); torch.cuda.set_stream(st)
+d8 = synth.d8_grid(a.n, a.n, device=dev); torch.cuda.synchronize()
+t0 = time.perf_counter(); plan = capi.Plan(dev_ptr=d8.data_ptr(), shape=(a.n, a.n)); t_plan = time.perf_counter() - t0
+del d8
+plan.set_stream(st.cuda_stream)
+print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan}), flush=True)
+for ld in [int(x) for x in a.batches.split(",")]:
+    A = torch.empty((a.n * a.n, ld), dtype=torch.float64, device=dev)
+    for fl in [int(x) for x in a.flags.split(",")]:
+        best = 1e30
+        for rep in range(3):
+            A.uniform_(0.0, 100.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); plan.accumulate_dev(A.data_ptr(), ld, ld, fl); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        units = a.n * a.n * ld
+        print(json.dumps({"ld": ld, "flags": fl, "ms": best, "cell_months_per_s": units / best * 1e3,
+                          "GBps_algorithmic": units * 16 / best * 1e3 / 1e9}), flush=True)
+    del A; torch.cuda.empty_cache()

@@ -38,11 +38,12 @@ def test_device_math_building_blocks(capi, oracle, rng):
         assert np.array_equal(capi.debug_math(5, v, np.full(v.size, float(d))), oracle.r_round(v, d))
     # exp on [0, 26], division, reciprocal cube root on [1, 2]: a few ulp
     e = rng.uniform(0, 26, 200000)
-    assert np.max(np.abs(capi.debug_math(2, e) / np.exp(e) - 1)) < 4e-16
+    assert np.max(np.abs(capi.debug_math(2, e) / np.exp(e) - 1)) < 7e-16      # <= 2 ulp + NumPy's own 1
     n, dd = rng.uniform(0, 5000, 200000), rng.uniform(2, 4e11, 200000)
-    assert np.max(np.abs(capi.debug_math(3, n, dd) / (n / dd) - 1)) < 3e-16
+    assert np.max(np.abs(capi.debug_math(3, n, dd) / (n / dd) - 1)) < 4.5e-16
+    assert np.max(np.abs(capi.debug_math(6, n, dd) / (n / dd) - 1)) < 4.5e-16      # the one-Newton-step variant in use
     c = rng.uniform(1, 2, 200000)
-    assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 4e-16
+    assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 7e-16
 
 
 @pytest.mark.parametrize("flags", [0, 16, 1, 17])
