@@ -254,16 +254,16 @@ def main():
     basin.set_stream(stream.cuda_stream)
     par_d = torch.from_numpy(par).to(dev)
     of_d = torch.empty(nloc, dtype=torch.float64, device=dev)
-    of_all = torch.empty(a.sets, dtype=torch.float64, device=dev) if world > 1 else of_d
     counts = [a.sets * (r + 1) // world - a.sets * r // world for r in range(world)]
+    mx = max(counts)
+    of_pad = torch.zeros(mx, dtype=torch.float64, device=dev)       # ragged slices padded for the all-gather
+    of_all = torch.empty(mx * world, dtype=torch.float64, device=dev) if world > 1 else of_d
 
     def step():
         basin.objective_batch_dev(par_d.data_ptr(), nloc, qobs, 36, capi.OF_KGE, flags, of_d.data_ptr())
         if world > 1:
-            if len(set(counts)) == 1:
-                dist.all_gather_into_tensor(of_all, of_d)
-            else:
-                dist.all_gather(list(of_all.split(counts)), of_d)
+            of_pad[:nloc].copy_(of_d)
+            dist.all_gather_into_tensor(of_all, of_pad)
 
     def fence():
         if world > 1:
@@ -296,6 +296,8 @@ def main():
     units_step = float(a.cells) * a.sets * a.months
     value = units_step * a.steps / (ms_total * 1e-3)
     of_host = of_all.cpu().numpy()
+    if world > 1:
+        of_host = np.concatenate([of_host.reshape(world, mx)[r, :c] for r, c in enumerate(counts)])
 
     # ---- roofline of the recursion kernel ------------------------------------------------------
     peak_tf = capi.fp64_peak_tflops(4096)

@@ -1,0 +1,186 @@
+"""Committed golden fixtures (tests/golden/*.npz, made by make_fixtures.py from the reference's bundled
+raw/ inputs) against the CPU oracle, and the host-side wrappers on top of an oracle-backed stub."""
+import datetime as dt
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import backend_stub
+from gr2msemidistr_b200 import api, gis, synth
+from gr2msemidistr_b200.rround import rround
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def c1():
+    return dict(np.load(os.path.join(G, "c1_inputs.npz"))), dict(np.load(os.path.join(G, "c1_golden.npz")))
+
+
+def _frame(inp):
+    n = len(inp["area"])
+    cols = {"DatesR": [f"{1981 + t // 12:04d}-{t % 12 + 1:02d}-01" for t in range(432)]}
+    for i, c in enumerate(inp["comid"]):
+        cols[f"P_{c}"] = inp["P"][i]
+    for i, c in enumerate(inp["comid"]):
+        cols[f"E_{c}"] = inp["E"][i]
+    cols["Q"] = inp["qobs"]
+    return pd.DataFrame(cols)
+
+
+def _subbasins(inp):
+    xy = inp["poly_xy"]
+    polys = [[xy[xy[:, 0] == i][:, 1:]] for i in range(len(inp["area"]))]
+    return gis.Subbasins(inp["area"], np.array(["A"] * len(inp["area"])), inp["comid"], polys)
+
+
+def test_fixture_matches_survey_facts(c1):
+    inp, gold = c1
+    # 13 subbasins, 432 months, 12 NA in qobs, DEM 251 x 429 with 15 934 nodata cells
+    assert inp["P"].shape == (13, 432) and inp["dem"].shape == (251, 429)
+    assert np.isnan(inp["qobs"]).sum() == 12 and (inp["dem"] == -32768).sum() == 15934
+    assert abs(inp["area"].sum() - 5379.2) < 0.1
+    assert np.array_equal(rround(inp["P"], 1), inp["P"])            # Create:114 rounds to 1 dp
+    assert np.array_equal(inp["ndays"], synth.ndays(432))
+
+
+def test_oracle_reproduces_golden(c1, oracle):
+    inp, gold = c1
+    reg = np.zeros(13, np.int32)
+    sim = oracle.run(inp["P"], inp["E"], inp["area"], inp["ndays"], reg, 1, gold["params0"])
+    for k in ("PR", "AE", "SM", "RU", "QS", "S_end", "R_end"):
+        assert np.array_equal(sim[k], gold[k]), k
+    assert np.array_equal(oracle.outlet_run(sim["QS"], sim["RU"], inp["area"], inp["ndays"]), gold["qt_run"])
+    pl = oracle.d8_plan(inp["flowdir"])
+    for k in ("level", "order", "level_off", "contam"):
+        assert np.array_equal(pl[k], gold[k]), k
+    qs = oracle.r_round(sim["QS"], 1)
+    assert np.array_equal(oracle.route(inp["flowdir"], qs, inp["src_cell"], inp["poly_off"], inp["poly_cells"]), gold["QR"])
+    ob = oracle.objective_batch(inp["P"][:, :264], inp["E"][:, :264], inp["area"], inp["ndays"][:264], reg, 1,
+                                gold["params"], inp["qobs"][:264], warmup=36, nthreads=4)
+    assert np.array_equal(ob["of"], gold["of"], equal_nan=True) and np.array_equal(ob["qt"], gold["qt"])
+
+
+def test_documented_example_has_exact_decimal_ties(c1, oracle):
+    # 1.186 * P hits exact decimal ties in the bundled example, so R's round matters
+    inp, gold = c1
+    tie = (np.rint(inp["P"] * 10).astype(np.int64) * 1186) % 1000 == 500
+    assert tie.sum() >= 3 and set(np.unique(inp["P"][tie])) >= {25.0, 75.0}
+    assert np.all(gold["PR"][inp["P"] == 25.0] == 29.6)                    # R: round(29.65, 1) = 29.6
+    half_up = np.floor(1.186 * inp["P"] * 10 + 0.5) / 10                   # C-style rounding says 29.7
+    assert np.any(half_up != gold["PR"])
+
+
+def test_run_wrapper_structure_and_rounding(c1, oracle):
+    inp, gold = c1
+    data, sb = _frame(inp), _subbasins(inp)
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=synth.SET0, backend=backend_stub)
+    assert list(m)[:9] == ["SINK", "QS", "RU", "PR", "AE", "SM", "Dates", "COMID", "EndState"]     # Run:256-264
+    assert m["QS"].shape == (432, 13) and m["Dates"][0] == dt.date(1981, 1, 1) and m["Dates"][-1] == dt.date(2016, 12, 1)
+    for k in ("PR", "AE", "SM", "RU", "QS"):
+        assert np.array_equal(m[k], oracle.r_round(gold[k].T, 1)), k
+    assert np.array_equal(m["SINK"]["sim"], oracle.r_round(gold["qt_run"], 3))
+    assert np.array_equal(m["SINK"]["obs"], oracle.r_round(inp["qobs"], 3), equal_nan=True)
+    assert abs(m["EndState"][4]["Store"]["Prod"] - gold["S_end"][4]) == 0
+    # WarmUp drops the first rows of everything (Run:240-251)
+    w = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", WarmUp=36, Parameters=synth.SET0, backend=backend_stub)
+    assert w["QS"].shape == (396, 13) and w["Dates"][0] == dt.date(1984, 1, 1)
+    assert np.array_equal(w["QS"], m["QS"][36:]) and np.array_equal(w["SINK"]["sim"], m["SINK"]["sim"][36:])
+    # a sub-period, then EndState -> IniState continues the run exactly (Run:151-179)
+    a = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1999", Parameters=synth.SET0, backend=backend_stub)
+    b = api.Run_GR2MSemiDistr(data, sb, "01/2000", "12/2016", Parameters=synth.SET0, IniState=a["EndState"],
+                              backend=backend_stub)
+    assert np.array_equal(np.vstack([a["QS"], b["QS"]]), m["QS"])
+    # without Q there is no SINK (Run:268-277); bad dates and parameter counts are rejected
+    noq = api.Run_GR2MSemiDistr(data.drop(columns="Q"), sb, "01/1981", "12/1981", Parameters=synth.SET0, backend=backend_stub)
+    assert "SINK" not in noq and noq["PR"].shape == (12, 13)
+    with pytest.raises(ValueError):
+        api.Run_GR2MSemiDistr(data, sb, "01/1975", "12/2016", Parameters=synth.SET0, backend=backend_stub)
+    with pytest.raises(ValueError):
+        api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=[1, 2, 3], backend=backend_stub)
+
+
+def test_run_wrapper_single_subbasin_branch(c1, oracle):
+    inp, _ = c1
+    data = _frame(inp).iloc[:, [0, 3, 16, 27]]            # DatesR, P_3, E_3, Q
+    sb = gis.Subbasins(inp["area"][2:3], np.array(["A"]), inp["comid"][2:3], [])
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1990", Parameters=synth.SET0, backend=backend_stub)
+    sim = oracle.run(inp["P"][2:3, :120], inp["E"][2:3, :120], inp["area"][2:3], inp["ndays"][:120], np.zeros(1, np.int32), 1, synth.SET0)
+    ru = oracle.r_round(sim["RU"][0], 1)
+    qs = oracle.r_round(inp["area"][2] * ru / (86.4 * inp["ndays"][:120]), 1)      # Run:195-200 uses the rounded ru
+    assert np.array_equal(m["QS"][:, 0], qs) and np.array_equal(m["SINK"]["sim"], oracle.r_round(qs, 3))
+
+
+def test_save_and_update_files(c1, tmp_path, monkeypatch):
+    inp, _ = c1
+    data, sb = _frame(inp), _subbasins(inp)
+    monkeypatch.chdir(tmp_path)
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "03/1981", Parameters=synth.SET0, Save=True, backend=backend_stub)
+    f = tmp_path / "Outputs" / "PR_GR2MSemiDistr_198103.txt"                      # Run:318-322
+    names, dates, mat = api._read_table(str(f))
+    assert names == [f"PR_{c}" for c in inp["comid"]] and dates == m["Dates"] and np.array_equal(mat, m["PR"])
+    # Update mode: append this month to last month's file and remove it (Run:282-316)
+    today = dt.date(1981, 6, 15)
+    os.rename(f, tmp_path / "Outputs" / "PR_GR2MSemiDistr_198104.txt")
+    for k in ("AE", "SM", "RU"):
+        os.rename(tmp_path / "Outputs" / f"{k}_GR2MSemiDistr_198103.txt", tmp_path / "Outputs" / f"{k}_GR2MSemiDistr_198104.txt")
+    nxt = api.Run_GR2MSemiDistr(data, sb, "04/1981", "04/1981", Parameters=synth.SET0, IniState=m["EndState"], backend=backend_stub)
+    api._save_run(nxt, "04/1981", True, outdir=str(tmp_path / "Outputs"), today=today)
+    names, dates, mat = api._read_table(str(tmp_path / "Outputs" / "PR_GR2MSemiDistr_198105.txt"))
+    assert len(dates) == 4 and np.array_equal(mat[3], nxt["PR"][0]) and not (tmp_path / "Outputs" / "PR_GR2MSemiDistr_198104.txt").exists()
+
+
+def test_routing_wrapper(c1, oracle):
+    inp, gold = c1
+    sb = _subbasins(inp)
+    dem = gis.Raster(np.where(inp["dem"] == -32768, -3e38, inp["dem"]).astype(np.float32)[None], *inp["dem_geo"], nodata=-3e38)
+    src, off, cells = api.routing_geometry(sb, dem)
+    assert np.array_equal(src, inp["src_cell"]) and np.array_equal(off, inp["poly_off"]) and np.array_equal(cells, inp["poly_cells"])
+    model = {"QS": oracle.r_round(gold["QS"].T, 1), "Dates": [dt.date(1981 + t // 12, t % 12 + 1, 1) for t in range(432)]}
+    r = api.Routing_GR2MSemiDistr(model, sb, dem, backend=backend_stub)           # derives FlowDir from the DEM
+    assert list(r)[:3] == ["QR", "Dates", "COMID"] and r["QR"].shape == (432, 13)
+    assert np.array_equal(r["QR"], oracle.r_round(gold["QR"].T, 1))
+    sub = api.Routing_GR2MSemiDistr(model, sb, dem, AcumIni="01/1990", AcumEnd="12/1990", FlowDir=inp["flowdir"], backend=backend_stub)
+    assert sub["QR"].shape == (12, 13) and np.array_equal(sub["QR"], r["QR"][108:120]) and sub["Dates"][0] == dt.date(1990, 1, 1)
+    # a routed discharge is at least the subbasin's own contribution when its source cell is interior and clean
+    assert np.all(r["QR"].max(axis=1) >= model["QS"].max(axis=1) - 0.05)
+
+
+def test_optim_wrapper_with_stub_backend(c1):
+    inp, _ = c1
+    data, sb = _frame(inp), _subbasins(inp)
+    res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
+                                  Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
+                                  Max_Functions=400, Optimization="KGE", ngs=4, backend=backend_stub)
+    assert res["Param"].shape == (4,) and np.array_equal(res["Param"], rround(res["Param"], 3))
+    assert np.all(res["Param"] >= [1, 0.01, 0.8, 0.8]) and np.all(res["Param"] <= [2000, 2, 1.2, 1.2])
+    with backend_stub.Basin(inp["P"][:, :264], inp["E"][:, :264], inp["area"], inp["ndays"][:264], np.zeros(13, np.int32), 1) as b:
+        start = 1.0 - b.objective_batch(np.array([[1000.0, 1, 1, 1]]), inp["qobs"][:264], 36, 0)["of"][0]
+        found = 1.0 - b.objective_batch(res["Param"][None], inp["qobs"][:264], 36, 0)["of"][0]
+    assert res["Value"] > start + 0.1     # the search improved on the documented starting point
+    assert abs(found - res["Value"]) <= 2e-3   # reported value is the objective at the (3-dp rounded) parameters
+    assert 400 <= res["evaluations"] < 400 + 3 * 4 * 9
+
+
+def test_optim_fixed_regions_are_spliced_back(oracle):
+    # two regions, region 'B' not optimised: its parameters stay put and bounds repeat per optimised region (Optim:78-90)
+    P, E, area, nd = synth.forcing(6, 60)
+    cols = {"DatesR": [f"{1981 + t // 12:04d}/{t % 12 + 1:02d}/01" for t in range(60)]}
+    for i in range(6):
+        cols[f"P_{i}"] = P[i]
+    for i in range(6):
+        cols[f"E_{i}"] = E[i]
+    region = np.array(["A", "B", "A", "B", "A", "A"])
+    rid = (region == "B").astype(np.int32)
+    truth = np.array([300.0, 800.0, 0.8, 1.1, 1.0, 0.9, 1.1, 1.05])
+    sim = oracle.run(P, E, area, nd, rid, 2, truth)
+    cols["Q"] = oracle.outlet_optim(sim["QS"])
+    sb = gis.Subbasins(area, region, np.arange(6), [])
+    start = np.array([1000.0, 800.0, 1.0, 1.1, 1.0, 0.9, 1.0, 1.05])
+    res = api.Optim_GR2MSemiDistr(pd.DataFrame(cols), sb, "01/1981", "12/1985", WarmUp=12, Parameters=start,
+                                  Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
+                                  Max_Functions=1500, Optimization="RMSE", No_Optim=["B"], ngs=6, backend=backend_stub)
+    assert np.array_equal(res["Param"][[1, 3, 5, 7]], truth[[1, 3, 5, 7]])
+    assert res["Value"] < 5.0
