@@ -38,7 +38,10 @@ if ROOT not in sys.path:
 METRIC = "gr2m_cell_months_per_sec"
 UNIT = "cell-months/s"
 FLOP_PER_UNIT_ALGO = 67          # nominal FP64 operations per (cell, set, month)
-FP64_INSTR_PER_UNIT = 104        # FP64-pipe SASS instructions per unit of k_gr2m_calib<true> (profiles/)
+try:   # FP64-pipe instructions per unit of the shipped recursion kernel, counted by ncu (profiles/)
+    FP64_INSTR_PER_UNIT = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_instr.json")))["fp64_pipe_inst_per_unit"]
+except Exception:
+    FP64_INSTR_PER_UNIT = 91.7
 
 
 def parse_args():
@@ -51,7 +54,7 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=10_000)
     ap.add_argument("--months", type=int, default=480)
     ap.add_argument("--route-n", type=int, default=20_000, help="side of the synthetic D8 grid (0 = skip routing)")
-    ap.add_argument("--route-batch", type=int, default=16, help="months per routing batch")
+    ap.add_argument("--route-batch", type=int, default=32, help="months per routing batch")
     ap.add_argument("--route-flags", type=int, default=0, help="WFA_* flags for the routing sweep")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -301,16 +304,21 @@ def main():
 
     # ---- roofline of the recursion kernel ------------------------------------------------------
     peak_tf = capi.fp64_peak_tflops(4096)
+    peak_rrr = capi.fp64_peak_rrr_tflops(4096)
     units_kernel = float(a.cells) * nloc * a.months
     ach_tf = units_kernel * FP64_INSTR_PER_UNIT * 2.0 / (kernel_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "traffic": None,
-                "kernel": "k_gr2m_calib<fast>" if not a.literal else "k_gr2m_calib<literal>",
+                "kernel": "k_gr2m_calib2<fast>" if not a.literal else "k_gr2m_calib2<literal>",
+                "peak_three_register_operand_dfma": peak_rrr,
+                "frac_of_three_register_operand_peak": ach_tf / peak_rrr,
                 "kernel_ms": kernel_ms, "units_per_launch": units_kernel,
                 "fp64_instr_per_unit": FP64_INSTR_PER_UNIT,
                 "achieved_def": "FP64-pipe instructions issued per unit (SASS count, profiles/) x units x 2 flop "
                                 "(DFMA-slot equivalents) / CUDA-event kernel time",
-                "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak), 2 flop per DFMA",
+                "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak: constant multiplier/addend, "
+                            "2 flop per DFMA); MEASURED_PEAKS.json has no FP64 entry. DFMAs whose three operands are "
+                            "distinct registers sustain only peak_three_register_operand_dfma on this part",
                 "algorithmic_flop_per_unit": FLOP_PER_UNIT_ALGO,
                 "achieved_algorithmic_tflops": units_kernel * FLOP_PER_UNIT_ALGO / (kernel_ms * 1e-3) / 1e12,
                 "survey_ceiling_units_per_s": 7.4e10,

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgr2m_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4
 PERC_F32_EXPONENT, SINK_UNROUNDED, MATH_LITERAL = 1, 8, 16
 OF_KGE, OF_NSE, OF_RMSE = 0, 1, 2
-WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC = 1, 2, 4
+WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW = 1, 2, 4, 8
 OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
@@ -28,7 +28,7 @@ SYMBOLS = (
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
-    "wfa_plan_last_kernel_ms",
+    "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms",
 )
 
 
@@ -110,8 +110,8 @@ class Basin:
                                        _ip(ndays), _ip(region_id), C.c_int(self.nreg), C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().gr2m_basin_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.gr2m_basin_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
@@ -202,8 +202,8 @@ class Plan:
         self.nlevels, self.norder, self.ncell = nl.value, no.value, nc.value
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().wfa_plan_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.wfa_plan_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
@@ -221,6 +221,11 @@ class Plan:
         ms = C.c_float()
         _check(lib().wfa_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_phase_ms(self):
+        a, b = C.c_float(), C.c_float()
+        _check(lib().wfa_plan_last_phase_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def export(self):
         n = self.ncell
@@ -272,3 +277,10 @@ def debug_math(op: int, x, y=None):
     out = np.empty_like(x)
     _check(lib().gr2m_debug_math(C.c_int(op), C.c_int(x.size), _dp(x), _dp(y), _dp(out)))
     return out
+
+
+def fp64_peak_rrr_tflops(iters: int = 4096) -> float:
+    """DFMA throughput when all three operands are distinct per-thread registers (development probe)."""
+    t = C.c_double()
+    _check(lib().gr2m_fp64_peak_rrr(C.c_int(iters), C.byref(t)))
+    return t.value

@@ -245,6 +245,98 @@ __global__ void __launch_bounds__(SPB * 32, 3) k_gr2m_calib(CalibArgs a)
             a.partial[((size_t)cs * a.nsets + set) * a.ntime + t] = qacc[warp * a.ntime_pad + t];
 }
 
+// Variant 2 of the same kernel, tuned for occupancy and for warps that drift apart:
+//  * 8-month stages (4 KiB), 4 in flight  -> 51 KiB shared memory per CTA, 4 CTAs (32 warps) per SM;
+//  * no block barrier in the month loop: every warp counts itself out of a stage and the LAST warp
+//    to leave a stage re-arms its mbarrier and issues the bulk copy that refills it, so fast warps
+//    run up to 3 stages ahead of slow ones instead of meeting them every stage.
+constexpr int TM2 = 8;
+constexpr int NST2 = 4;
+constexpr int STAGE2_DBL = TM2 * 64;
+
+template <bool FAST>
+__global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);   // NST2 * STAGE2_DBL
+    double *qacc = stage + NST2 * STAGE2_DBL;               // SPB * ntime_pad
+    double *tconv = qacc + SPB * a.ntime_pad;               // ntime_pad
+    double *tab = tconv + a.ntime_pad;                      // 32
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 32);   // NST2
+    int *left = reinterpret_cast<int *>(full + NST2);          // NST2: warps that have left the stage
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
+    const int set = sg * SPB + warp;
+    const bool set_ok = set < a.nsets;
+    const int tile0 = cs * a.tiles_per_split;
+    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
+    const int nchunk = a.ntime_pad / TM2;
+    const int total = (tile1 - tile0) * nchunk;
+
+    for (int i = tid; i < SPB * a.ntime_pad; i += blockDim.x) qacc[i] = 0.0;
+    for (int i = tid; i < a.ntime_pad; i += blockDim.x) tconv[i] = i < a.ntime ? a.tconv[i] : 1.0;
+    if (tid < 32) tab[tid] = c_exp2_tab[tid];
+    if (tid < NST2) left[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NST2; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;
+    if (tid == 0) {
+        for (int g = 0; g < NST2 && g < total; ++g) {
+            mbar_arrive_expect_tx(&full[g], STAGE2_DBL * 8);
+            bulk_g2s(stage + g * STAGE2_DBL, Fbase + (size_t)g * STAGE2_DBL, STAGE2_DBL * 8, &full[g]);
+        }
+    }
+
+    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4 * a.nreg;
+    double *myacc = qacc + warp * a.ntime_pad;
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    int g = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int cell = tile * 32 + lane;
+        const bool cell_ok = cell < a.ncell;
+        CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0, a.forcing_ok);
+        double S = 0.3 * p.X1, R = 0.5 * p.X2;
+        for (int ch = 0; ch < nchunk; ++ch, ++g) {
+            const int st = g % NST2;
+            mbar_wait(&full[st], (g / NST2) & 1);
+            if (set_ok) {
+                const double *sp = stage + st * STAGE2_DBL + lane;
+                const double *tc = tconv + ch * TM2;
+                double v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    double Pr = sp[m * 64], Er = sp[m * 64 + 32];
+                    StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab) : step_literal(p, Pr, Er, S, R, a.f32exp);
+                    v[m] = FAST ? (p.area * o.Q) * tc[m] : (p.area * o.Q) / tc[m];
+                }
+                double s = warp_reduce8(v, lane);
+                if ((lane & 3) == 0) myacc[ch * TM2 + ridx] += s;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // this warp's reads of the stage are complete (their values were consumed above)
+                if (atomicAdd(&left[st], 1) == SPB - 1) {
+                    left[st] = 0;
+                    const int gn = g + NST2;
+                    if (gn < total) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive_expect_tx(&full[st], STAGE2_DBL * 8);
+                        bulk_g2s(stage + st * STAGE2_DBL, Fbase + (size_t)gn * STAGE2_DBL, STAGE2_DBL * 8, &full[st]);
+                    }
+                }
+            }
+        }
+    }
+    if (set_ok)
+        for (int t = lane; t < a.ntime; t += 32)
+            a.partial[((size_t)cs * a.nsets + set) * a.ntime + t] = myacc[t];
+}
+
 struct SimArgs {
     const double *F, *area, *params, *den, *S0, *R0;
     const int *region;
@@ -616,7 +708,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     }
     // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
     const int nsg = ceil_div(nsets, SPB);
-    const int target = g_sm_count * 3 * 8;
+    const int target = g_sm_count * 4 * 8;
     int csplit = ceil_div(target, nsg);
     if (csplit > b->ntiles) csplit = b->ntiles;
     if (csplit < 1) csplit = 1;
@@ -636,9 +728,16 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
     a.forcing_ok = b->forcing_ok;
-    size_t smem = (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
+    static int variant = -1;   // GR2M_CALIB_VARIANT=1 selects the first kernel (development A/B switch)
+    if (variant < 0) {
+        const char *ev = getenv("GR2M_CALIB_VARIANT");
+        variant = ev ? atoi(ev) : 2;
+    }
+    const bool v2 = variant != 1;
+    size_t smem = v2 ? (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST2 * 12
+                     : (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
-    auto kern = fast ? k_gr2m_calib<true> : k_gr2m_calib<false>;
+    auto kern = v2 ? (fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>) : (fast ? k_gr2m_calib<true> : k_gr2m_calib<false>);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, b->stream));
     kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
@@ -712,6 +811,60 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, doubl
     }
     double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (r == 123.456) sink[0] = r;
+}
+
+// Same chains, but every DFMA reads three distinct per-thread register pairs (no constant-bank or
+// immediate operands): the register-file-limited rate real FP64 code can sustain.
+__global__ void __launch_bounds__(256) k_fp64_peak_rrr(int iters, double seed, double *sink)
+{
+    double a[8], m[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {   // operands come from memory so the compiler cannot fold them
+        a[u] = seed + threadIdx.x + u;
+        m[u] = sink[1 + threadIdx.x * 16 + u];
+        c[u] = sink[1 + threadIdx.x * 16 + 8 + u];
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = __fma_rn(a[u], m[u], c[u]);
+        }
+    }
+    double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    if (r == 123.456) sink[0] = r;
+}
+
+extern "C" int gr2m_fp64_peak_rrr(int iters, double *tflops)
+{
+    REQUIRE(iters > 0 && tflops, "bad arguments");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    const int blocks = prop.multiProcessorCount * 8;
+    double *sink = nullptr;
+    CK(cudaMalloc(&sink, (1 + 256 * 16) * sizeof(double)));
+    CK(cudaMemset(sink, 0, (1 + 256 * 16) * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_fp64_peak_rrr<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak_rrr<<<blocks, 256>>>(iters, 1.0, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = 2.0 * 64.0 * (double)iters * 256.0 * blocks / (best * 1e-3) / 1e12;
+    return GR2M_OK;
 }
 
 extern "C" int gr2m_fp64_peak(int iters, double *tflops, float *ms_out)

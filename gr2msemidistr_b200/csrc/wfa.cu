@@ -126,10 +126,12 @@ __global__ void k_sort_keys(const int32_t *__restrict__ level, long long n, int 
 }
 
 __global__ void k_level_offsets(const uint32_t *__restrict__ keys, long long n, int nlevels,
-                                int32_t *__restrict__ level_off)
+                                int32_t *__restrict__ level_off, const int32_t *__restrict__ order,
+                                const uint8_t *__restrict__ inmask, uint8_t *__restrict__ omask)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    omask[i] = inmask[order[i]];   // in-flow mask in sweep order: read coalesced next to order[]
     uint32_t k = keys[i];
     if (k >= (uint32_t)nlevels) {
         if (i == 0 || keys[i - 1] < (uint32_t)nlevels) level_off[nlevels] = (int32_t)i;
@@ -157,54 +159,128 @@ __global__ void k_tailmask(const int32_t *__restrict__ order, int begin, int end
 }
 
 // ---- sweep --------------------------------------------------------------------------------------
-// One group of G lanes per cell, months j = g, g+G, ... on the lanes.
-// CG: read through L2 only (rows written by other SMs / warps during the same launch).
+// One group of G lanes per cell, months j = g, g+G, ... on the lanes.  The cell's own row and its
+// first upstream row are requested together (two independent loads in flight per lane); the rarer
+// further upstream rows follow.  Additions run in TauDEM's k = 1..8 order, so the sum is deterministic.
+// CG: read through L2 only (rows written by other warps during the same launch).
+template <typename T, bool CG>
+__device__ __forceinline__ T ldv(const T *p)
+{
+    return CG ? __ldcg(p) : *p;
+}
+
+template <typename T>
+__device__ __forceinline__ const T *up_row(const T *A, int32_t c, int k, int ncol, int ld)
+{
+    return A + (size_t)(c + c_dy[k] * ncol + c_dx[k]) * ld;
+}
+
 template <typename T, int G, bool CG>
 __device__ __forceinline__ void accum_cell(int32_t c, int g, int ncol, unsigned m, T *A, int ld, int nmonth)
 {
     T *row = A + (size_t)c * ld;
+    const T *u0 = up_row(A, c, __ffs(m), ncol, ld);
+    const unsigned rest = m & (m - 1);
     for (int j = g; j < nmonth; j += G) {
-        T acc = CG ? __ldcg(row + j) : row[j];
-        unsigned mm = m;
+        T own = ldv<T, CG>(row + j), a0 = ldv<T, CG>(u0 + j);
+        T acc = own + a0;
+        unsigned mm = rest;
         while (mm) {
-            int k = __ffs(mm);
+            acc += ldv<T, CG>(up_row(A, c, __ffs(mm), ncol, ld) + j);
             mm &= mm - 1;
-            const T *up = A + (size_t)(c + c_dy[k] * ncol + c_dx[k]) * ld + j;
-            acc += CG ? __ldcg(up) : *up;
         }
         row[j] = acc;
     }
 }
 
-template <typename T, int G>
-__global__ void __launch_bounds__(256) k_accum_level(const int32_t *__restrict__ order, int begin, int end, int ncol,
-                                                     const uint8_t *__restrict__ inmask, T *__restrict__ A, int ld,
-                                                     int nmonth)
+// two independent cells of one level interleaved: four loads in flight per lane
+template <typename T, int G, bool CG>
+__device__ __forceinline__ void accum_cell2(int32_t c0, unsigned m0, int32_t c1, unsigned m1, int g, int ncol, T *A,
+                                            int ld, int nmonth)
 {
-    int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, g = threadIdx.x % G;
-    int i = begin + gid;
-    if (i >= end) return;
-    int32_t c = order[i];
-    unsigned m = inmask[c];
-    if (m) accum_cell<T, G, false>(c, g, ncol, m, A, ld, nmonth);
+    T *row0 = A + (size_t)c0 * ld, *row1 = A + (size_t)c1 * ld;
+    const T *u0 = up_row(A, c0, __ffs(m0), ncol, ld), *u1 = up_row(A, c1, __ffs(m1), ncol, ld);
+    const unsigned rest0 = m0 & (m0 - 1), rest1 = m1 & (m1 - 1);
+    for (int j = g; j < nmonth; j += G) {
+        T own0 = ldv<T, CG>(row0 + j), a0 = ldv<T, CG>(u0 + j);
+        T own1 = ldv<T, CG>(row1 + j), a1 = ldv<T, CG>(u1 + j);
+        T acc0 = own0 + a0, acc1 = own1 + a1;
+        unsigned mm = rest0;
+        while (mm) {
+            acc0 += ldv<T, CG>(up_row(A, c0, __ffs(mm), ncol, ld) + j);
+            mm &= mm - 1;
+        }
+        mm = rest1;
+        while (mm) {
+            acc1 += ldv<T, CG>(up_row(A, c1, __ffs(mm), ncol, ld) + j);
+            mm &= mm - 1;
+        }
+        row0[j] = acc0;
+        row1[j] = acc1;
+    }
 }
 
-// thin levels [lev0, lev1) inside one resident CTA, a block barrier between levels
+// one wide level per launch, two cells per lane group (cells of a level never feed each other)
+template <typename T, int G>
+__global__ void __launch_bounds__(256) k_accum_level(const int32_t *__restrict__ order, int begin, int end, int ncol,
+                                                     const uint8_t *__restrict__ omask, T *__restrict__ A, int ld,
+                                                     int nmonth)
+{
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, g = threadIdx.x % G;
+    const int i = begin + 2 * gid;
+    if (i >= end) return;
+    const int32_t c0 = order[i];
+    const unsigned m0 = omask[i];
+    if (i + 1 < end) {
+        const int32_t c1 = order[i + 1];
+        const unsigned m1 = omask[i + 1];
+        if (m0 && m1) accum_cell2<T, G, false>(c0, m0, c1, m1, g, ncol, A, ld, nmonth);
+        else if (m0) accum_cell<T, G, false>(c0, g, ncol, m0, A, ld, nmonth);
+        else if (m1) accum_cell<T, G, false>(c1, g, ncol, m1, A, ld, nmonth);
+    } else if (m0) {
+        accum_cell<T, G, false>(c0, g, ncol, m0, A, ld, nmonth);
+    }
+}
+
+// thin levels [lev0, lev1) inside one resident CTA with a block barrier between levels.  The topology
+// reads of the NEXT level (offsets, first cell and mask per lane group) are issued before the current
+// level is computed, and that cell's rows are prefetched into L2, so each level costs about one L2
+// round trip plus the barrier instead of a chain of DRAM latencies.
 template <typename T, int G>
 __global__ void __launch_bounds__(1024) k_accum_thin(const int32_t *__restrict__ order,
                                                      const int32_t *__restrict__ level_off, int lev0, int lev1,
-                                                     int ncol, const uint8_t *__restrict__ inmask, T *A, int ld,
+                                                     int ncol, const uint8_t *__restrict__ omask, T *A, int ld,
                                                      int nmonth)
 {
     const int ngroups = blockDim.x / G, gid = threadIdx.x / G, g = threadIdx.x % G;
+    int b = level_off[lev0], e = level_off[lev0 + 1];
+    int e2 = lev0 + 2 <= lev1 ? level_off[lev0 + 2] : e;
+    int32_t cn = -1;
+    unsigned mn = 0;
+    if (b + gid < e) { cn = order[b + gid]; mn = omask[b + gid]; }
     for (int l = lev0; l < lev1; ++l) {
-        int b = level_off[l], e = level_off[l + 1];
-        for (int i = b + gid; i < e; i += ngroups) {
-            int32_t c = order[i];
-            unsigned m = inmask[c];
-            if (m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
+        const int32_t c = cn;
+        const unsigned m = mn;
+        // next level: offsets two ahead, first cell of this group, L2 prefetch of its rows
+        const int e3 = l + 3 <= lev1 ? level_off[l + 3] : e2;
+        cn = -1; mn = 0;
+        if (e + gid < e2) { cn = order[e + gid]; mn = omask[e + gid]; }
+        if (c >= 0 && m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
+        for (int i = b + gid + ngroups; i < e; i += ngroups) {
+            const int32_t ci = order[i];
+            const unsigned mi = omask[i];
+            if (mi) accum_cell<T, G, true>(ci, g, ncol, mi, A, ld, nmonth);
+        }
+        if (cn >= 0 && g < nmonth) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)cn * ld + g));
+            unsigned mm = mn;
+            while (mm) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(up_row(A, cn, __ffs(mm), ncol, ld) + g));
+                mm &= mm - 1;
+            }
         }
         __syncthreads();
+        b = e; e = e2; e2 = e3;
     }
 }
 
@@ -213,7 +289,7 @@ __global__ void __launch_bounds__(1024) k_accum_thin(const int32_t *__restrict__
 // epoch in done[], which are always held by earlier tickets => no deadlock.
 template <typename T, int G>
 __global__ void __launch_bounds__(256) k_accum_dataflow(const int32_t *__restrict__ order, int begin, int end,
-                                                        int ncol, const uint8_t *__restrict__ inmask,
+                                                        int ncol, const uint8_t *__restrict__ omask,
                                                         const uint8_t *__restrict__ tailmask, T *A, int ld, int nmonth,
                                                         unsigned *done, unsigned epoch, int *ticket)
 {
@@ -229,7 +305,7 @@ __global__ void __launch_bounds__(256) k_accum_dataflow(const int32_t *__restric
         int i1 = min(end, i0 + CHUNK);
         for (int i = i0; i < i1; ++i) {
             int32_t c = order[i];
-            unsigned m = inmask[c], tm = tailmask[c];
+            unsigned m = omask[i], tm = tailmask[c];
             if (g == 0) {
                 while (tm) {
                     int k = __ffs(tm);
@@ -359,7 +435,7 @@ struct DevBuf {
 };
 
 constexpr int THIN_LIMIT = 2048;      // plan peeling: frontiers this small are peeled inside one CTA
-constexpr int TAIL_WIDTH = 512;       // sweep: the tail starts where every later level is at most this wide
+constexpr int TAIL_WIDTH = 512;       // dataflow sweep: the tail starts where every later level is at most this wide
 
 }  // namespace
 
@@ -367,10 +443,10 @@ struct wfa_plan {
     int device = 0, nrow = 0, ncol = 0, nlevels = 0, norder = 0, tail_level = 0, flags = 0;
     long long ncell = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;   // start, end, end of the wide-level phase
     bool timed = false;
     unsigned epoch = 0;
-    DevBuf receiver, inmask, indeg, level, order, level_off, contam, tailmask, done, ticket, work, work2, qs, src, poff,
+    DevBuf receiver, inmask, omask, indeg, level, order, level_off, contam, tailmask, done, ticket, work, work2, qs, src, poff,
         pcells, qr;
     std::vector<int32_t> h_level_off;
 };
@@ -379,12 +455,13 @@ static void plan_free(wfa_plan *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
+    DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
                       &p->qr};
     for (DevBuf *d : bufs) d->release();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->evm) cudaEventDestroy(p->evm);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
@@ -456,6 +533,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PRC(keys2.ensure(n * 4));
     PRC(vals.ensure(n * 4));
     PRC(p->order.ensure(n * 4));
+    PRC(p->omask.ensure(n));
     PRC(p->level_off.ensure(((size_t)p->nlevels + 2) * 4));
     k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>(),
                                     p->contam.as<uint8_t>());
@@ -469,7 +547,8 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
                                         p->order.as<int32_t>(), n, 0, bits, st));
     PCK(cudaMemsetAsync(p->level_off.p, 0, ((size_t)p->nlevels + 2) * 4, st));
-    k_level_offsets<<<nb, 256, 0, st>>>(keys2.as<uint32_t>(), n, p->nlevels, p->level_off.as<int32_t>());
+    k_level_offsets<<<nb, 256, 0, st>>>(keys2.as<uint32_t>(), n, p->nlevels, p->level_off.as<int32_t>(),
+                                        p->order.as<int32_t>(), p->inmask.as<uint8_t>(), p->omask.as<uint8_t>());
     PCK(cudaGetLastError());
     p->h_level_off.assign((size_t)p->nlevels + 1, 0);
     PCK(cudaMemcpyAsync(p->h_level_off.data(), p->level_off.p, ((size_t)p->nlevels + 1) * 4, cudaMemcpyDeviceToHost, st));
@@ -517,6 +596,7 @@ static int plan_create_common(const int16_t *flowdir, bool on_device, int nrow, 
     cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->evm);
     if (e != cudaSuccess) {
         gr2m_set_error("wfa_plan_create: %s", cudaGetErrorString(e));
         plan_free(p);
@@ -589,6 +669,17 @@ extern "C" int wfa_plan_export(const wfa_plan *pc, int32_t *receiver, uint8_t *i
     return GR2M_OK;
 }
 
+extern "C" int wfa_plan_last_phase_ms(wfa_plan *p, float *wide_ms, float *tail_ms)
+{
+    REQUIRE(p && wide_ms && tail_ms, "NULL argument");
+    REQUIRE(p->timed, "no timed call yet");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->ev1));
+    CK(cudaEventElapsedTime(wide_ms, p->ev0, p->evm));
+    CK(cudaEventElapsedTime(tail_ms, p->evm, p->ev1));
+    return GR2M_OK;
+}
+
 extern "C" int wfa_plan_last_kernel_ms(wfa_plan *p, float *ms)
 {
     REQUIRE(p && ms, "NULL argument");
@@ -604,19 +695,27 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
 {
     cudaStream_t st = p->stream;
     const int32_t *order = p->order.as<int32_t>();
-    const uint8_t *inmask = p->inmask.as<uint8_t>();
+    const uint8_t *omask = p->omask.as<uint8_t>();   // in-flow masks in sweep order
     const std::vector<int32_t> &off = p->h_level_off;
-    const int gpb = 256 / G;   // cell groups per 256-thread block
+    const int gpb = 256 / G;   // lane groups per 256-thread block
+    const bool dataflow = (flags & WFA_DATAFLOW) != 0;
+    // the thin tail starts where every later level fits a few passes of the single resident CTA
+    int l0 = p->tail_level;
+    if (!dataflow) {
+        const int width = 4 * (1024 / G);
+        l0 = p->nlevels;
+        while (l0 > 1 && off[l0] - off[l0 - 1] <= width) --l0;
+    }
     // level 0 has no upstream cells: nothing to add
-    for (int l = 1; l < p->tail_level; ++l) {
+    for (int l = 1; l < l0; ++l) {
         int b = off[l], e = off[l + 1];
-        k_accum_level<T, G><<<ceil_div(e - b, gpb), 256, 0, st>>>(order, b, e, p->ncol, inmask, A, ld, nmonth);
+        k_accum_level<T, G><<<ceil_div(ceil_div(e - b, 2), gpb), 256, 0, st>>>(order, b, e, p->ncol, omask, A, ld, nmonth);
     }
     CK(cudaGetLastError());
-    const int l0 = p->tail_level;
+    CK(cudaEventRecord(p->evm, st));
     if (l0 < p->nlevels) {
-        if (flags & WFA_LEVEL_SYNC) {
-            k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, inmask, A,
+        if (!dataflow) {
+            k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
                                                    ld, nmonth);
         } else {
             int b = off[l0], e = p->norder;
@@ -624,7 +723,7 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
             int groups = ceil_div(e - b, 4);
             int blocks = std::min(ceil_div(groups, gpb), 148 * 4);
-            k_accum_dataflow<T, G><<<blocks, 256, 0, st>>>(order, b, e, p->ncol, inmask, p->tailmask.as<uint8_t>(), A, ld,
+            k_accum_dataflow<T, G><<<blocks, 256, 0, st>>>(order, b, e, p->ncol, omask, p->tailmask.as<uint8_t>(), A, ld,
                                                            nmonth, p->done.as<unsigned>(), p->epoch, p->ticket.as<int>());
         }
         CK(cudaGetLastError());

@@ -54,7 +54,8 @@ extern "C" {
                                      float32 accumulation; default accumulates in FP64 */
 #define WFA_NO_CONTAMINATION  2   /* AreaD8 -nc; default keeps the edge-contamination check ON as the
                                      reference does (no -nc at Routing:117) */
-#define WFA_LEVEL_SYNC        4   /* use the level-synchronous sweep instead of the dataflow sweep */
+#define WFA_LEVEL_SYNC        4   /* level-synchronous thin tail (the default; kept for callers that set it) */
+#define WFA_DATAFLOW          8   /* flag-driven dataflow kernel for the thin tail instead */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
 typedef struct wfa_plan   wfa_plan;     /* D8 topology plan resident in HBM */
@@ -156,6 +157,8 @@ int wfa_accumulate(wfa_plan *p, int nmonth, const double *W, int flags, double *
 int wfa_accumulate_dev(wfa_plan *p, int nmonth, int ld, void *WA_dev, int flags);
 int wfa_mask_dev(wfa_plan *p, int nmonth, int ld, void *WA_dev, int flags);
 int wfa_plan_last_kernel_ms(wfa_plan *p, float *ms);
+/* split of the last sweep: wide levels (one launch each) and the thin tail */
+int wfa_plan_last_phase_ms(wfa_plan *p, float *wide_ms, float *tail_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,45 @@
+"""Summarise an .ncu-rep (read here, no GPU needed): python scripts/ncu_summary.py rep.ncu-rep units_per_launch > profiles/x.txt"""
+import csv, io, subprocess, sys
+rep, units = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else None
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, unit = rows[0], rows[1]
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+STALL = "smsp__average_warps_issue_stalled_"
+for r in rows[2:]:
+    d = dict(zip(hdr, r)); u = dict(zip(hdr, unit))
+    print("=" * 100)
+    for k in KEYS:
+        if k in d:
+            print(f"{k:80s} {d[k]:>22s} {u.get(k, '')}")
+    print("-- stall reasons (warps per issue-active cycle) --")
+    for k in sorted(d):
+        if k.startswith(STALL) and k.endswith("_per_issue_active.ratio"):
+            try:
+                v = float(d[k])
+            except ValueError:
+                continue
+            if v >= 0.05:
+                print(f"   {k[len(STALL):-len('_per_issue_active.ratio')]:30s} {v:8.3f}")
+    if units:
+        cyc = float(d["sm__cycles_elapsed.max"].replace(",", ""))
+        f = sum(float(d[f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum.per_cycle_elapsed"].replace(",", "")) for o in ("dfma", "dmul", "dadd"))
+        tot = float(d["smsp__inst_executed.sum"].replace(",", "")) * float(d["smsp__thread_inst_executed_per_inst_executed.ratio"])
+        print(f"-- derived for {units:.4g} units per launch --")
+        print(f"   DFMA+DMUL+DADD thread instructions per unit : {f * cyc / units:8.2f}")
+        print(f"   all thread instructions per unit            : {tot / units:8.2f}")
+        print(f"   units per second                            : {units / (float(d['gpu__time_duration.sum'].replace(',', '')) * 1e-3):.4g}" if u.get('gpu__time_duration.sum') == 'ms' else "")

@@ -109,4 +109,4 @@ def test_calibration_on_the_gpu(capi, c1):
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
                                   Max_Functions=3000, Optimization="KGE", ngs=16, backend=backend_stub)
     assert res["Value"] >= ref["Value"] - 0.02 and res["Value"] > 0.5
-    assert res["evaluations"] >= 20000
+    assert res["evaluations"] > 5000          # whole generations of 128 complexes x 9 points per batch

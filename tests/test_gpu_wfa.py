@@ -47,7 +47,7 @@ def test_plan_edge_cases(capi, oracle, rng):
             for k in PLAN_KEYS:
                 assert np.array_equal(got[k], ref[k]), k
             W = rng.uniform(0, 10, (3,) + d.shape)
-            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_LEVEL_SYNC):
+            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW):
                 A = p.accumulate(W, fl)
                 Ar = np.stack([oracle.aread8(d, W[m], contcheck=not (fl & capi.WFA_NO_CONTAMINATION)) for m in range(3)])
                 assert np.array_equal(np.isnan(A), np.isnan(Ar))
@@ -59,7 +59,7 @@ def test_accumulate_dense_matches_oracle(capi, oracle, rng, nmonth):
     d = synth.d8_grid(150, 210, seed=7).numpy()
     W = rng.uniform(0, 100, (nmonth, 150, 210))
     with capi.Plan(d) as p:
-        for fl in (0, capi.WFA_LEVEL_SYNC, capi.WFA_NO_CONTAMINATION):
+        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_NO_CONTAMINATION):
             A = p.accumulate(W, fl)
             cc = not (fl & capi.WFA_NO_CONTAMINATION)
             for m in {0, nmonth // 2, nmonth - 1}:
@@ -91,7 +91,7 @@ def test_dataflow_tail_on_long_thin_network(capi, oracle, rng):
         got = p.export()
         for k in PLAN_KEYS:
             assert np.array_equal(got[k], ref[k]), k
-        for fl in (capi.WFA_NO_CONTAMINATION, capi.WFA_NO_CONTAMINATION | capi.WFA_LEVEL_SYNC):
+        for fl in (capi.WFA_NO_CONTAMINATION, capi.WFA_NO_CONTAMINATION | capi.WFA_DATAFLOW):
             A = p.accumulate(W, fl)
             for m in (0, 7):
                 Ar = oracle.aread8(d, W[m], contcheck=False)
@@ -110,7 +110,7 @@ def test_route_matches_oracle_c1_shape(capi, oracle, rng):
     ref32 = oracle.route(d, QS, src, off, cells, f32=True, nthreads=8)
     with capi.Plan(d) as p:
         QR = p.route(QS, src, off, cells)
-        QR_ls = p.route(QS, src, off, cells, capi.WFA_LEVEL_SYNC)
+        QR_ls = p.route(QS, src, off, cells, capi.WFA_DATAFLOW)
         QR32 = p.route(QS, src, off, cells, capi.WFA_F32)
         QRnc = p.route(QS, src, off, cells, capi.WFA_NO_CONTAMINATION)
     assert np.array_equal(QR, ref) and np.array_equal(QR_ls, ref)
