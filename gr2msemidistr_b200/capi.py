@@ -27,7 +27,7 @@ SYMBOLS = (
     "gr2m_basin_create", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
-    "wfa_plan_export", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
+    "wfa_plan_export", "wfa_plan_basin_info", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
     "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms",
 )
 
@@ -221,6 +221,11 @@ class Plan:
         ms = C.c_float()
         _check(lib().wfa_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def basin_info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().wfa_plan_basin_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(cut_level=a.value, nbasins=b.value, nupper=c.value, enabled=bool(d.value))
 
     def last_phase_ms(self):
         a, b = C.c_float(), C.c_float()

@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
     double *stage = reinterpret_cast<double *>(smem_raw);   // NST2 * STAGE2_DBL
     double *qacc = stage + NST2 * STAGE2_DBL;               // SPB * ntime_pad
     double *tconv = qacc + SPB * a.ntime_pad;               // ntime_pad
-    double *tab = tconv + a.ntime_pad;                      // 32
-    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 32);   // NST2
+    double *tab = tconv + a.ntime_pad;                      // 256: 2^(j/256)
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 256);   // NST2
     int *left = reinterpret_cast<int *>(full + NST2);          // NST2: warps that have left the stage
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
 
     for (int i = tid; i < SPB * a.ntime_pad; i += blockDim.x) qacc[i] = 0.0;
     for (int i = tid; i < a.ntime_pad; i += blockDim.x) tconv[i] = i < a.ntime ? a.tconv[i] : 1.0;
-    if (tid < 32) tab[tid] = c_exp2_tab[tid];
+    tab[tid] = c_exp2_tab256[tid];   // blockDim.x == 256
     if (tid < NST2) left[tid] = 0;
     if (tid == 0) {
         for (int i = 0; i < NST2; ++i) mbar_init(&full[i], 1);
@@ -311,11 +311,15 @@ __global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     double Pr = sp[m * 64], Er = sp[m * 64 + 32];
-                    StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab) : step_literal(p, Pr, Er, S, R, a.f32exp);
-                    v[m] = FAST ? (p.area * o.Q) * tc[m] : (p.area * o.Q) / tc[m];
+                    if (FAST) {
+                        v[m] = p.area * step_fast2(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
+                    } else {
+                        StepOut o = step_literal(p, Pr, Er, S, R, a.f32exp);
+                        v[m] = (p.area * o.Q) / tc[m];
+                    }
                 }
                 double s = warp_reduce8(v, lane);
-                if ((lane & 3) == 0) myacc[ch * TM2 + ridx] += s;
+                if ((lane & 3) == 0) myacc[ch * TM2 + ridx] += FAST ? s * tc[ridx] : s;
             }
             __syncwarp();
             if (lane == 0) {
@@ -458,8 +462,9 @@ __global__ void __launch_bounds__(128) k_objective(ObjArgs a)
 // 4 rcbrt_fast, 5 r_round_dig(x, (int)y))
 __global__ void k_debug_math(int op, int n, const double *x, const double *y, double *out)
 {
-    __shared__ double tab[32];
+    __shared__ double tab[32], tab256[256];
     if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    tab256[threadIdx.x & 255] = c_exp2_tab256[threadIdx.x & 255];
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -471,6 +476,9 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 3: r = div_fast(x[i], y[i]); break;
         case 4: r = rcbrt_fast(x[i]); break;
         case 6: r = div_fast1(x[i], y[i]); break;
+        case 7: r = div_fast3(x[i], y[i]); break;
+        case 8: r = exp_tab256(x[i], tab256); break;
+        case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;
@@ -734,7 +742,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         variant = ev ? atoi(ev) : 2;
     }
     const bool v2 = variant != 1;
-    size_t smem = v2 ? (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST2 * 12
+    size_t smem = v2 ? (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 256) * sizeof(double) + NST2 * 12
                      : (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
     auto kern = v2 ? (fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>) : (fast ? k_gr2m_calib<true> : k_gr2m_calib<false>);

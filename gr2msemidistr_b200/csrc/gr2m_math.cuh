@@ -24,6 +24,11 @@ __constant__ double c_exp2_tab[32] = {
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 
+// 2^(j/256), j = 0..255: the table the hot kernels stage in shared memory (2 KiB)
+__constant__ double c_exp2_tab256[256] = {
+#include "exp2_tab256.inc"
+};
+
 #define GR2M_MAGIC 6755399441055744.0   /* 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51 */
 
 // 64-bit literals that do not fit an instruction immediate.  Kept in constant memory so DFMA/DMUL
@@ -31,7 +36,7 @@ __constant__ double c_exp2_tab[32] = {
 // (the first build spent ~60 of its ~200 instructions per month on such moves).
 struct MathK {
     double magic, nmagic, tenth, inv_ln2_32, nln2_32_hi, ln2_32_lo, c6, c5, c4, c3, two_ninths, third, tie_thr,
-        nf32_delta;
+        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo;
 };
 __constant__ MathK KC = {GR2M_MAGIC,
                          -GR2M_MAGIC,
@@ -46,7 +51,10 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          0x1.c71c71c71c71cp-3,    // 2/9
                          0x1.5555555555555p-2,    // 1/3
                          0.499,
-                         -9.9341074625651041667e-9};   // -((double)(1.f/3.f) - 1/3)
+                         -9.9341074625651041667e-9,   // -((double)(1.f/3.f) - 1/3)
+                         0x1.71547652b82fep+8,        // 256 / ln 2
+                         -0x1.62e42fefa0000p-9,       // -(ln2/256) high part (38 significant bits)
+                         -0x1.cf79abc9e3b3ap-48};     // -(ln2/256) low part
 
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
@@ -80,6 +88,17 @@ __device__ __forceinline__ double r_round1(double x, double thr)
 {
     double x10 = __dmul_rn(x, 10.0);
     double n = __dadd_rn(__dadd_rn(x10, KC.magic), KC.nmagic);
+    double f = __dsub_rn(x10, n);
+    if (!(fabs(f) < thr)) return r_round1_exact(x);
+    return div10_rn(n);
+}
+
+// Same, with rint(10x) taken by the conversion unit (F2I + I2F on the XU pipe) instead of two DADDs on
+// the FP64 pipe.  |10x| >= 2^31 saturates the conversion, which makes |f| huge and falls to the exact path.
+__device__ __forceinline__ double r_round1_cvt(double x, double thr)
+{
+    double x10 = __dmul_rn(x, 10.0);
+    double n = (double)__double2int_rn(x10);
     double f = __dsub_rn(x10, n);
     if (!(fabs(f) < thr)) return r_round1_exact(x);
     return div10_rn(n);
@@ -122,6 +141,23 @@ __device__ __forceinline__ double exp_tab(double x, const double *__restrict__ t
     return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
 }
 
+// Same scheme with a 256-entry table: |r| <= ln2/512 = 1.35e-3, degree-4 Taylor (remainder 3.8e-17),
+// 9 FP64-pipe instructions instead of 11.
+__device__ __forceinline__ double exp_tab256(double x, const double *__restrict__ tab)
+{
+    double t = __fma_rn(x, KC.inv_ln2_256, KC.magic);
+    int ki = __double2loint(t);
+    double kd = __dadd_rn(t, KC.nmagic);
+    double r = __fma_rn(kd, KC.nln2_256_hi, x);
+    r = __fma_rn(kd, KC.nln2_256_lo, r);
+    double p = __fma_rn(r, KC.c4, KC.c3);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    double v = __dmul_rn(p, tab[ki & 255]);
+    return __hiloint2double(__double2hiint(v) + ((ki >> 8) << 20), __double2loint(v));
+}
+
 __device__ __forceinline__ double rcp_seed(double d)
 {
     double r;
@@ -153,6 +189,17 @@ __device__ __forceinline__ double div_fast1(double n, double d)
     double q = __dmul_rn(n, r);
     double rem = __fma_rn(-d, q, n);
     return __fma_rn(rem, r, q);
+}
+
+// cubic (Halley-type) refinement of the seed, no residual correction: r1 = r0 (1 + e + e^2), e = 1 - d r0;
+// 4 FP64-pipe instructions, error ~ e^3 + 1.5 ulp.  Needs a seed good to ~2^-18 (checked in tests).
+__device__ __forceinline__ double div_fast3(double n, double d)
+{
+    double r = rcp_seed(d);
+    double e = __fma_rn(-d, r, 1.0);
+    double t = __fma_rn(e, e, e);
+    r = __fma_rn(r, t, r);
+    return __dmul_rn(n, r);
 }
 
 // c^(-1/3) for c in [1, 2] (works for any normal c > 0): FP32 MUFU seed (~2^-21), one Halley step
@@ -220,6 +267,44 @@ __device__ __forceinline__ StepOut step_fast(const CellPar &p, double Praw, doub
     o.Pc = Pc;
     o.Q = Q;
     return o;
+}
+
+// Leaner formulation used by the calibration kernel (bit-level differences from step_fast are at the
+// ulp level): 256-entry exp table, conversion-unit rint in the forcing correction, halved
+// tanh terms (ah = (a-1)/2 etc. via FMA with immediates, which removes the S1+S1 add), one division
+// step less.  Returns Q only; `tab` is the 256-entry table.
+__device__ __forceinline__ double step_fast2(const CellPar &p, double Praw, double Eraw, double &S, double &R,
+                                             bool f32exp, const double *__restrict__ tab)
+{
+    // forcing correction for P and E together: one tie test and one (rare) branch per month
+    double xp = __dmul_rn(p.fp, Praw), xe = __dmul_rn(p.fe, Eraw);
+    double xp10 = __dmul_rn(xp, 10.0), xe10 = __dmul_rn(xe, 10.0);
+    double np_ = (double)__double2int_rn(xp10), ne_ = (double)__double2int_rn(xe10);
+    double fp_ = __dsub_rn(xp10, np_), fe_ = __dsub_rn(xe10, ne_);
+    double Pc = div10_rn(np_), Ec = div10_rn(ne_);
+    if (!(fabs(fp_) < p.thr) || !(fabs(fe_) < p.thr)) {
+        Pc = r_round1_exact(xp);
+        Ec = r_round1_exact(xe);
+    }
+    double a = exp_tab256(clamp26(Pc * p.i2X1), tab);
+    double b = exp_tab256(clamp26(Ec * p.i2X1), tab);
+    // S1 = (S (a+1) + X1 (a-1)) / ((a+1) + s (a-1)), numerator and denominator both halved
+    double am = __fma_rn(a, 0.5, -0.5), ap = __fma_rn(a, 0.5, 0.5);
+    double s = S * p.iX1;
+    double S1 = div_fast1(__fma_rn(p.X1, am, S * ap), __fma_rn(s, am, ap));
+    double P1 = (Pc + S) - S1;
+    // S2 = 2 S1 / ((b+1) + (1 - S1/X1)(b-1)) = S1 / ((b+1)/2 + (1 - S1/X1)(b-1)/2)
+    double bm = __fma_rn(b, 0.5, -0.5), bp = __fma_rn(b, 0.5, 0.5);
+    double S2 = div_fast1(S1, __fma_rn(__fma_rn(S1, -p.iX1, 1.0), bm, bp));
+    double sr = S2 * p.iX1;
+    double c = __fma_rn(sr * sr, sr, 1.0);
+    double y = rcbrt_fast(c);
+    if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
+    S = S2 * y;
+    double R2 = p.X2 * (R + (P1 + (S2 - S)));
+    double Q = div_fast1(R2 * R2, R2 + 60.0);
+    R = R2 - Q;
+    return Q;
 }
 
 __device__ __forceinline__ StepOut step_literal(const CellPar &p, double Praw, double Eraw, double &S,

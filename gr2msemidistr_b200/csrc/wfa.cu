@@ -15,6 +15,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -284,6 +286,112 @@ __global__ void __launch_bounds__(1024) k_accum_thin(const int32_t *__restrict__
     }
 }
 
+
+// ---- upper forest by outlet basin ---------------------------------------------------------------
+// Above a cut level the network is a forest of independent trees (one per outlet / sink).  Cells of
+// the upper forest are regrouped by tree: corder[] = cells sorted by (root, level, id), so one CTA
+// sweeps one tree level by level with only block barriers, and many trees run concurrently.
+__global__ void k_root_init(const int32_t *__restrict__ order, int ub, int nu, const int32_t *__restrict__ receiver,
+                            int32_t *__restrict__ root)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = order[ub + i], r = receiver[c];
+    root[c] = r >= 0 ? r : c;
+}
+
+__global__ void k_root_jump(const int32_t *__restrict__ order, int ub, int nu, int32_t *root)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = order[ub + i];
+    int32_t r = ((volatile int32_t *)root)[c];
+    root[c] = ((volatile int32_t *)root)[r];      // racing readers only ever see an ancestor
+}
+
+__global__ void k_root_keys(const int32_t *__restrict__ order, int ub, int nu, const int32_t *__restrict__ root,
+                            uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = order[ub + i];
+    keys[i] = (uint32_t)root[c];
+    vals[i] = c;
+}
+
+// cmask, level-start flags; component starts are appended to a list (any order)
+__global__ void k_comp_flags(const int32_t *__restrict__ corder, const uint32_t *__restrict__ ckeys, int nu,
+                             const int32_t *__restrict__ level, const uint8_t *__restrict__ inmask,
+                             uint8_t *__restrict__ cmask, uint8_t *__restrict__ lstart, int32_t *__restrict__ comp_beg,
+                             int *__restrict__ ncomp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = corder[i];
+    cmask[i] = inmask[c];
+    bool newc = i == 0 || ckeys[i] != ckeys[i - 1];
+    bool newl = newc || level[c] != level[corder[i - 1]];
+    lstart[i] = newl ? (newc ? 2 : 1) : 0;
+    if (newc) comp_beg[atomicAdd(ncomp, 1)] = i;
+}
+
+// cnext[i] (defined at level starts): position of the next level start or component start
+__global__ void k_comp_next(const uint8_t *__restrict__ lstart, int nu, int32_t *__restrict__ cnext)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu || !lstart[i]) return;
+    int j = i + 1;
+    while (j < nu && !lstart[j]) ++j;
+    cnext[i] = j;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256) k_accum_components(const int32_t *__restrict__ corder,
+                                                          const uint8_t *__restrict__ cmask,
+                                                          const int32_t *__restrict__ cnext,
+                                                          const int2 *__restrict__ comps, int ncomp, int *ticket,
+                                                          int ncol, T *A, int ld, int nmonth)
+{
+    __shared__ int s_k;
+    const int ngroups = 256 / G, gid = threadIdx.x / G, g = threadIdx.x % G;
+    for (;;) {
+        if (threadIdx.x == 0) s_k = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int k = s_k;
+        __syncthreads();
+        if (k >= ncomp) return;
+        int pos = comps[k].x;
+        const int ce = comps[k].y;
+        int e = cnext[pos];
+        int32_t cn = -1;
+        unsigned mn = 0;
+        if (pos + gid < e) { cn = corder[pos + gid]; mn = cmask[pos + gid]; }
+        while (pos < ce) {
+            const int32_t c = cn;
+            const unsigned m = mn;
+            const int e2 = e < ce ? cnext[e] : ce;          // issued before this level's work
+            cn = -1; mn = 0;
+            if (e + gid < e2) { cn = corder[e + gid]; mn = cmask[e + gid]; }
+            if (c >= 0 && m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
+            for (int i = pos + gid + ngroups; i < e; i += ngroups) {
+                const int32_t ci = corder[i];
+                const unsigned mi = cmask[i];
+                if (mi) accum_cell<T, G, true>(ci, g, ncol, mi, A, ld, nmonth);
+            }
+            if (cn >= 0 && g < nmonth) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)cn * ld + g));
+                unsigned mm = mn;
+                while (mm) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(up_row(A, cn, __ffs(mm), ncol, ld) + g));
+                    mm &= mm - 1;
+                }
+            }
+            __syncthreads();
+            pos = e; e = e2;
+        }
+    }
+}
+
 // dataflow tail: cells order[begin, end) are claimed in order, one ticket per sub-warp group and
 // CHUNK cells per ticket; a cell waits only for tail upstream cells (tailmask) to publish their
 // epoch in done[], which are always held by earlier tickets => no deadlock.
@@ -434,6 +542,7 @@ struct DevBuf {
     template <typename T> T *as() { return static_cast<T *>(p); }
 };
 
+constexpr int COMP_WIDTH = 16384;     // per-basin sweep starts where every later level is at most this wide
 constexpr int THIN_LIMIT = 2048;      // plan peeling: frontiers this small are peeled inside one CTA
 constexpr int TAIL_WIDTH = 512;       // dataflow sweep: the tail starts where every later level is at most this wide
 
@@ -449,6 +558,10 @@ struct wfa_plan {
     DevBuf receiver, inmask, omask, indeg, level, order, level_off, contam, tailmask, done, ticket, work, work2, qs, src, poff,
         pcells, qr;
     std::vector<int32_t> h_level_off;
+    // upper forest regrouped by outlet basin (see k_accum_components)
+    int comp_level = 0, ncomp = 0, nupper = 0;
+    bool comp_ok = false;
+    DevBuf corder, cmask, cnext, comps;
 };
 
 static void plan_free(wfa_plan *p)
@@ -457,7 +570,7 @@ static void plan_free(wfa_plan *p)
     cudaSetDevice(p->device);
     DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
-                      &p->qr};
+                      &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps};
     for (DevBuf *d : bufs) d->release();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -465,6 +578,8 @@ static void plan_free(wfa_plan *p)
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
+
+static int plan_build_components(wfa_plan *p);
 
 static int plan_build(wfa_plan *p, const int16_t *dir_dev)
 {
@@ -576,8 +691,92 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(st));
+    return plan_build_components(p);
+}
+
+// Regroup the upper forest (levels >= comp_level) by outlet basin.  Falls back to the level-wide
+// sweep (comp_ok = false) when the forest does not split into enough comparable trees.
+static int plan_build_components(wfa_plan *p)
+{
+    cudaStream_t st = p->stream;
+    const std::vector<int32_t> &off = p->h_level_off;
+    int comp_width = COMP_WIDTH;
+    if (const char *ev = getenv("WFA_COMP_WIDTH")) comp_width = atoi(ev);   // development knob
+    int lc = p->nlevels;
+    while (lc > 1 && off[lc] - off[lc - 1] <= comp_width) --lc;
+    p->comp_level = lc;
+    p->comp_ok = false;
+    if (lc >= p->nlevels) return GR2M_OK;
+    const int ub = off[lc], nu = p->norder - ub;
+    if (nu <= 0) return GR2M_OK;
+    p->nupper = nu;
+    const long long n = p->ncell;
+    const int nb = ceil_div(nu, 256);
+    int rc;
+    DevBuf root, keys, keys2, vals, temp, lstart, cbeg, cnt;
+    auto cleanup = [&]() { root.release(); keys.release(); keys2.release(); vals.release(); temp.release();
+                           lstart.release(); cbeg.release(); cnt.release(); };
+#define QCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+#define QRC(call) do { int r_ = (call); if (r_) { cleanup(); return r_; } } while (0)
+    QRC(root.ensure(n * 4));
+    QRC(keys.ensure((size_t)nu * 4));
+    QRC(keys2.ensure((size_t)nu * 4));
+    QRC(vals.ensure((size_t)nu * 4));
+    QRC(lstart.ensure(nu));
+    QRC(cbeg.ensure((size_t)nu * 4));
+    QRC(cnt.ensure(sizeof(int)));
+    QRC(p->corder.ensure((size_t)nu * 4));
+    QRC(p->cmask.ensure(nu));
+    QRC(p->cnext.ensure((size_t)nu * 4));
+    const int32_t *order = p->order.as<int32_t>();
+    k_root_init<<<nb, 256, 0, st>>>(order, ub, nu, p->receiver.as<int32_t>(), root.as<int32_t>());
+    int depth = p->nlevels - lc + 1, jumps = 1;
+    while ((1 << jumps) < depth) ++jumps;
+    for (int it = 0; it < jumps + 1; ++it) k_root_jump<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>());
+    k_root_keys<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>(), keys.as<uint32_t>(), vals.as<int32_t>());
+    QCK(cudaGetLastError());
+    int bits = 1;
+    while ((1ll << bits) < n) ++bits;
+    size_t tbytes = 0;
+    QCK(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
+                                        p->corder.as<int32_t>(), nu, 0, bits, st));
+    QRC(temp.ensure(tbytes ? tbytes : 16));
+    QCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
+                                        p->corder.as<int32_t>(), nu, 0, bits, st));
+    QCK(cudaMemsetAsync(cnt.p, 0, sizeof(int), st));
+    k_comp_flags<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), keys2.as<uint32_t>(), nu, p->level.as<int32_t>(),
+                                     p->inmask.as<uint8_t>(), p->cmask.as<uint8_t>(), lstart.as<uint8_t>(),
+                                     cbeg.as<int32_t>(), cnt.as<int>());
+    k_comp_next<<<nb, 256, 0, st>>>(lstart.as<uint8_t>(), nu, p->cnext.as<int32_t>());
+    QCK(cudaGetLastError());
+    int ncomp = 0;
+    QCK(cudaMemcpyAsync(&ncomp, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QCK(cudaStreamSynchronize(st));
+    std::vector<int32_t> beg(ncomp);
+    if (ncomp) QCK(cudaMemcpy(beg.data(), cbeg.p, (size_t)ncomp * 4, cudaMemcpyDeviceToHost));
+    std::sort(beg.begin(), beg.end());
+    std::vector<int2> comps(ncomp);
+    int largest = 0;
+    for (int k = 0; k < ncomp; ++k) {
+        comps[k].x = beg[k];
+        comps[k].y = k + 1 < ncomp ? beg[k + 1] : nu;
+        largest = std::max(largest, comps[k].y - comps[k].x);
+    }
+    std::stable_sort(comps.begin(), comps.end(), [](const int2 &a, const int2 &b) { return a.y - a.x > b.y - b.x; });
+    p->ncomp = ncomp;
+    if (ncomp > 0) {
+        rc = p->comps.ensure((size_t)ncomp * sizeof(int2));
+        if (rc) { cleanup(); return rc; }
+        QCK(cudaMemcpy(p->comps.p, comps.data(), (size_t)ncomp * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    // worth it only if the forest splits into many trees none of which dominates
+    p->comp_ok = ncomp >= 32 && (long long)largest * 8 <= nu;
+    cleanup();
+#undef QCK
+#undef QRC
     return GR2M_OK;
 }
+
 
 static int plan_create_common(const int16_t *flowdir, bool on_device, int nrow, int ncol, int flags, wfa_plan **out)
 {
@@ -652,6 +851,16 @@ extern "C" int wfa_plan_info(const wfa_plan *p, int *nlevels, int *norder, int64
     return GR2M_OK;
 }
 
+extern "C" int wfa_plan_basin_info(const wfa_plan *p, int *cut_level, int *nbasins, int *nupper, int *enabled)
+{
+    REQUIRE(p != nullptr, "plan is NULL");
+    if (cut_level) *cut_level = p->comp_level;
+    if (nbasins) *nbasins = p->ncomp;
+    if (nupper) *nupper = p->nupper;
+    if (enabled) *enabled = p->comp_ok ? 1 : 0;
+    return GR2M_OK;
+}
+
 extern "C" int wfa_plan_export(const wfa_plan *pc, int32_t *receiver, uint8_t *inmask, int32_t *indeg, int32_t *level,
                                int32_t *order, int32_t *level_off, uint8_t *contam)
 {
@@ -699,9 +908,12 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     const std::vector<int32_t> &off = p->h_level_off;
     const int gpb = 256 / G;   // lane groups per 256-thread block
     const bool dataflow = (flags & WFA_DATAFLOW) != 0;
+    const bool by_basin = p->comp_ok && !dataflow && !(flags & WFA_LEVEL_SYNC);
     // the thin tail starts where every later level fits a few passes of the single resident CTA
     int l0 = p->tail_level;
-    if (!dataflow) {
+    if (by_basin) {
+        l0 = p->comp_level;
+    } else if (!dataflow) {
         const int width = 4 * (1024 / G);
         l0 = p->nlevels;
         while (l0 > 1 && off[l0] - off[l0 - 1] <= width) --l0;
@@ -714,7 +926,13 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->evm, st));
     if (l0 < p->nlevels) {
-        if (!dataflow) {
+        if (by_basin) {
+            CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
+            int blocks = std::min(p->ncomp, 148 * 8);
+            k_accum_components<T, G><<<blocks, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(),
+                                                             p->cnext.as<int32_t>(), p->comps.as<int2>(), p->ncomp,
+                                                             p->ticket.as<int>(), p->ncol, A, ld, nmonth);
+        } else if (!dataflow) {
             k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
                                                    ld, nmonth);
         } else {

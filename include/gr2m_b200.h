@@ -54,7 +54,8 @@ extern "C" {
                                      float32 accumulation; default accumulates in FP64 */
 #define WFA_NO_CONTAMINATION  2   /* AreaD8 -nc; default keeps the edge-contamination check ON as the
                                      reference does (no -nc at Routing:117) */
-#define WFA_LEVEL_SYNC        4   /* level-synchronous thin tail (the default; kept for callers that set it) */
+#define WFA_LEVEL_SYNC        4   /* sweep the upper levels grid-wide (one launch / one CTA per level) instead of
+                                     per outlet basin, which is the default when the forest splits well */
 #define WFA_DATAFLOW          8   /* flag-driven dataflow kernel for the thin tail instead */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
@@ -133,6 +134,9 @@ int wfa_plan_destroy(wfa_plan *p);
 int wfa_plan_set_stream(wfa_plan *p, void *cuda_stream);
 /* sizes: number of levels, number of cells in the level order, number of cells */
 int wfa_plan_info(const wfa_plan *p, int *nlevels, int *norder, int64_t *ncell);
+/* per-outlet-basin regrouping of the upper levels: cut level, number of basins (trees), cells above the
+ * cut, and whether the sweep uses it (it needs >= 32 basins, none holding more than 1/8 of those cells) */
+int wfa_plan_basin_info(const wfa_plan *p, int *cut_level, int *nbasins, int *nupper, int *enabled);
 /* Copy the integer topology back (any pointer may be NULL): receiver/indeg/level [ncell] int32,
  * inmask/contam [ncell] uint8, order [norder], level_off [nlevels+1]. */
 int wfa_plan_export(const wfa_plan *p, int32_t *receiver, uint8_t *inmask, int32_t *indeg,

@@ -17,7 +17,7 @@ d8 = synth.d8_grid(a.n, a.n, device=dev); torch.cuda.synchronize()
 t0 = time.perf_counter(); plan = capi.Plan(dev_ptr=d8.data_ptr(), shape=(a.n, a.n)); t_plan = time.perf_counter() - t0
 del d8
 plan.set_stream(st.cuda_stream)
-print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan}), flush=True)
+print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan, "basins": plan.basin_info()}), flush=True)
 for ld in [int(x) for x in a.batches.split(",")]:
     A = torch.empty((a.n * a.n, ld), dtype=torch.float64, device=dev)
     for fl in [int(x) for x in a.flags.split(",")]:

@@ -47,7 +47,7 @@ def test_plan_edge_cases(capi, oracle, rng):
             for k in PLAN_KEYS:
                 assert np.array_equal(got[k], ref[k]), k
             W = rng.uniform(0, 10, (3,) + d.shape)
-            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW):
+            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC):
                 A = p.accumulate(W, fl)
                 Ar = np.stack([oracle.aread8(d, W[m], contcheck=not (fl & capi.WFA_NO_CONTAMINATION)) for m in range(3)])
                 assert np.array_equal(np.isnan(A), np.isnan(Ar))
@@ -59,7 +59,7 @@ def test_accumulate_dense_matches_oracle(capi, oracle, rng, nmonth):
     d = synth.d8_grid(150, 210, seed=7).numpy()
     W = rng.uniform(0, 100, (nmonth, 150, 210))
     with capi.Plan(d) as p:
-        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_NO_CONTAMINATION):
+        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_NO_CONTAMINATION):
             A = p.accumulate(W, fl)
             cc = not (fl & capi.WFA_NO_CONTAMINATION)
             for m in {0, nmonth // 2, nmonth - 1}:
@@ -138,6 +138,23 @@ def test_route_edge_cases(capi, oracle, rng):
         bad = src.copy(); bad[0] = nrow * ncol
         with pytest.raises(capi.GR2MError):
             p.route(QS, bad, off, cells)
+
+
+def test_per_basin_sweep_is_used_and_bit_identical(capi, oracle, rng):
+    # a grid that splits into many outlet basins: the default sweep regroups the upper levels by basin;
+    # it must give the same bits as the grid-wide level sweep and as the oracle
+    nrow, ncol = 900, 1200
+    d = synth.d8_grid(nrow, ncol, seed=5).numpy()
+    W = rng.uniform(0, 100, (33, nrow, ncol))
+    with capi.Plan(d) as p:
+        info = p.basin_info()
+        assert info["enabled"] and info["nbasins"] >= 32 and info["nupper"] > 0
+        A = p.accumulate(W, capi.WFA_NO_CONTAMINATION)
+        B = p.accumulate(W, capi.WFA_NO_CONTAMINATION | capi.WFA_LEVEL_SYNC)
+    assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(B, nan=-1))
+    for m in (0, 32):
+        Ar = oracle.aread8(d, W[m], contcheck=False)
+        assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(Ar, nan=-1))
 
 
 def test_linearity_and_mass_conservation_large(capi, rng):
