@@ -156,6 +156,29 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def cpu_routing(a):
+    """CPU oracle AreaD8 on a bounded dense sample, one month per host thread (TauDEM's own
+    parallelism is 8 MPI ranks per month, R/Routing_GR2MSemiDistr.R:117)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import oracle
+    from gr2msemidistr_b200 import synth
+    oracle.build()
+    n = min(a.route_n, 3000)
+    nthreads = os.cpu_count() or 1
+    d8 = synth.d8_grid(n, n).numpy()
+    rng = np.random.default_rng(7)
+    W = [rng.uniform(0, 100, (n, n)) for _ in range(nthreads)]
+    oracle.aread8(d8, W[0], contcheck=False)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(nthreads) as ex:
+        list(ex.map(lambda w: oracle.aread8(d8, w, contcheck=False), W))
+    dt = time.perf_counter() - t0
+    return {"value": n * n * nthreads / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"{n} x {n} grid of the same generator x {nthreads} months, {dt:.1f} s, orc_aread8 (Kahn queue, FP64), "
+                      f"one month per thread"}
+
+
 def bench_routing(a, capi, torch, rank, world, dist):
     """Secondary metric: batched WFA sweep, months sharded across ranks (plan replicated)."""
     from gr2msemidistr_b200 import synth
@@ -208,9 +231,12 @@ def bench_routing(a, capi, torch, rank, world, dist):
            "plan_build_s": t_plan, "grid_gen_s": t_gen,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "traffic": None, "algorithmic_bytes_per_unit": 16}}
+    out["basins"] = plan.basin_info()
     plan.close()
     del A
     torch.cuda.empty_cache()
+    if rank == 0 and not a.no_cpu:
+        out["cpu_baseline"] = cpu_routing(a)
     return out
 
 

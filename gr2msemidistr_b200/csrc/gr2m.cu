@@ -118,8 +118,10 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
                                             bool forcing_ok)
 {
     CellPar p;
-    p.X1 = fmax(par[reg], 0.01);             // RunModel_GR2M.R floors X1, X2 at 1e-2
-    p.X2 = fmax(par[nreg + reg], 0.01);
+    p.X1 = par[reg];                         // RunModel_GR2M.R floors X1, X2 at 1e-2 (NaN stays NaN)
+    p.X2 = par[nreg + reg];
+    if (p.X1 < 0.01) p.X1 = 0.01;
+    if (p.X2 < 0.01) p.X2 = 0.01;
     p.fp = par[2 * nreg + reg];
     p.fe = par[3 * nreg + reg];
     p.iX1 = 1.0 / p.X1;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
 
@@ -195,6 +196,25 @@ __device__ __forceinline__ void accum_cell(int32_t c, int g, int ncol, unsigned 
     }
 }
 
+// latency-critical variant for the per-basin / thin sweeps: EVERY upstream row is requested before any
+// addition (up to 9 independent L2 loads in flight), then added in k order.
+template <typename T, int G>
+__device__ __forceinline__ void accum_cell_all(int32_t c, int g, int ncol, unsigned m, T *A, int ld, int nmonth)
+{
+    T *row = A + (size_t)c * ld;
+    for (int j = g; j < nmonth; j += G) {
+        T v[8];
+        T acc = __ldcg(row + j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m & (1u << k)) v[k] = __ldcg(up_row(A, c, k + 1, ncol, ld) + j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m & (1u << k)) acc += v[k];
+        row[j] = acc;
+    }
+}
+
 // two independent cells of one level interleaved: four loads in flight per lane
 template <typename T, int G, bool CG>
 __device__ __forceinline__ void accum_cell2(int32_t c0, unsigned m0, int32_t c1, unsigned m1, int g, int ncol, T *A,
@@ -335,6 +355,28 @@ __global__ void k_comp_flags(const int32_t *__restrict__ corder, const uint32_t 
     if (newc) comp_beg[atomicAdd(ncomp, 1)] = i;
 }
 
+// upstream cell ids of every upper cell in k = 1..8 order (CSR): the sweep reads ready-made row indices
+__global__ void k_comp_upcount(const uint8_t *__restrict__ cmask, int nu, int32_t *__restrict__ cnt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nu) cnt[i] = __popc(cmask[i]);
+}
+
+__global__ void k_comp_upfill(const int32_t *__restrict__ corder, const uint8_t *__restrict__ cmask, int nu, int ncol,
+                              const int32_t *__restrict__ cup_off, int32_t *__restrict__ cup_idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = corder[i];
+    unsigned m = cmask[i];
+    int q = cup_off[i];
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        cup_idx[q++] = c + c_dy[k] * ncol + c_dx[k];
+    }
+}
+
 // cnext[i] (defined at level starts): position of the next level start or component start
 __global__ void k_comp_next(const uint8_t *__restrict__ lstart, int nu, int32_t *__restrict__ cnext)
 {
@@ -345,50 +387,115 @@ __global__ void k_comp_next(const uint8_t *__restrict__ lstart, int nu, int32_t 
     cnext[i] = j;
 }
 
+// CTA = 8 compute warps (256 threads, 256/G lane groups) + 1 prefetch warp.  The compute warps walk
+// one basin level by level (named barrier 1 between levels).  The upper phase is a latency chain as
+// long as the longest river, so the per-level path is kept short: upstream cells come as ready-made
+// ids (CSR cup_off / cup_idx, k order), and each lane group fetches the ids of its first cell of the
+// NEXT level while it works on the current one; the prefetch warp runs PF_AHEAD cells ahead through
+// the same list and pulls every row the sweep will touch into L2.
+constexpr int PF_AHEAD = 384;
+
+struct UpCell {           // first cell of a lane group in a level, with up to 3 upstream ids preloaded
+    int32_t c, b, n, u0, u1, u2;
+};
+
+__device__ __forceinline__ UpCell load_upcell(const int32_t *__restrict__ corder, const int32_t *__restrict__ cup_off,
+                                              const int32_t *__restrict__ cup_idx, int i, bool valid)
+{
+    UpCell x;
+    x.c = -1; x.b = 0; x.n = 0; x.u0 = x.u1 = x.u2 = 0;
+    if (valid) {
+        x.c = corder[i];
+        x.b = cup_off[i];
+        x.n = cup_off[i + 1] - x.b;
+        x.u0 = cup_idx[x.b];                       // n >= 1 above level 0
+        x.u1 = x.n > 1 ? cup_idx[x.b + 1] : 0;
+        x.u2 = x.n > 2 ? cup_idx[x.b + 2] : 0;
+    }
+    return x;
+}
+
 template <typename T, int G>
-__global__ void __launch_bounds__(256) k_accum_components(const int32_t *__restrict__ corder,
-                                                          const uint8_t *__restrict__ cmask,
+__device__ __forceinline__ void accum_upcell(const UpCell &x, const int32_t *__restrict__ cup_idx, int g, T *A, int ld,
+                                             int nmonth)
+{
+    T *row = A + (size_t)x.c * ld;
+    const T *r0 = A + (size_t)x.u0 * ld, *r1 = A + (size_t)x.u1 * ld, *r2 = A + (size_t)x.u2 * ld;
+    for (int j = g; j < nmonth; j += G) {
+        T own = __ldcg(row + j), a0 = __ldcg(r0 + j), a1 = 0, a2 = 0;
+        if (x.n > 1) a1 = __ldcg(r1 + j);
+        if (x.n > 2) a2 = __ldcg(r2 + j);
+        T acc = own + a0;
+        if (x.n > 1) acc += a1;
+        if (x.n > 2) acc += a2;
+        for (int q = 3; q < x.n; ++q) acc += __ldcg(A + (size_t)cup_idx[x.b + q] * ld + j);
+        row[j] = acc;
+    }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(288) k_accum_components(const int32_t *__restrict__ corder,
+                                                          const int32_t *__restrict__ cup_off,
+                                                          const int32_t *__restrict__ cup_idx,
                                                           const int32_t *__restrict__ cnext,
                                                           const int2 *__restrict__ comps, int ncomp, int *ticket,
-                                                          int ncol, T *A, int ld, int nmonth)
+                                                          T *A, int ld, int nmonth)
 {
-    __shared__ int s_k;
+    __shared__ int s_k, s_pos;
     const int ngroups = 256 / G, gid = threadIdx.x / G, g = threadIdx.x % G;
+    const bool prefetcher = threadIdx.x >= 256;
+    const int lane = threadIdx.x & 31;
+    const int row_bytes = nmonth * (int)sizeof(T);
     for (;;) {
-        if (threadIdx.x == 0) s_k = atomicAdd(ticket, 1);
+        if (threadIdx.x == 0) {
+            s_k = atomicAdd(ticket, 1);
+            s_pos = s_k < ncomp ? comps[s_k].x : 0;
+        }
         __syncthreads();
         const int k = s_k;
-        __syncthreads();
         if (k >= ncomp) return;
         int pos = comps[k].x;
         const int ce = comps[k].y;
-        int e = cnext[pos];
-        int32_t cn = -1;
-        unsigned mn = 0;
-        if (pos + gid < e) { cn = corder[pos + gid]; mn = cmask[pos + gid]; }
-        while (pos < ce) {
-            const int32_t c = cn;
-            const unsigned m = mn;
-            const int e2 = e < ce ? cnext[e] : ce;          // issued before this level's work
-            cn = -1; mn = 0;
-            if (e + gid < e2) { cn = corder[e + gid]; mn = cmask[e + gid]; }
-            if (c >= 0 && m) accum_cell<T, G, true>(c, g, ncol, m, A, ld, nmonth);
-            for (int i = pos + gid + ngroups; i < e; i += ngroups) {
-                const int32_t ci = corder[i];
-                const unsigned mi = cmask[i];
-                if (mi) accum_cell<T, G, true>(ci, g, ncol, mi, A, ld, nmonth);
-            }
-            if (cn >= 0 && g < nmonth) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)cn * ld + g));
-                unsigned mm = mn;
-                while (mm) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(up_row(A, cn, __ffs(mm), ncol, ld) + g));
-                    mm &= mm - 1;
+        if (prefetcher) {
+            for (int i = pos + lane; i < ce; i += 32) {
+                while (i > *(volatile int *)&s_pos + PF_AHEAD) __nanosleep(64);
+                const char *r = reinterpret_cast<const char *>(A + (size_t)corder[i] * ld);
+                for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + bb));
+                for (int q = cup_off[i]; q < cup_off[i + 1]; ++q) {
+                    const char *u = reinterpret_cast<const char *>(A + (size_t)cup_idx[q] * ld);
+                    for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + bb));
                 }
             }
-            __syncthreads();
-            pos = e; e = e2;
+        } else {
+            int e = cnext[pos];
+            UpCell nx = load_upcell(corder, cup_off, cup_idx, pos + gid, pos + gid < e);
+            while (pos < ce) {
+                const int e2 = e < ce ? cnext[e] : ce;          // issued before this level's work
+                // cells pos+gid, pos+gid+ngroups, ... of this level; the ids of the following cell (or of
+                // this group's first cell of the next level) are always requested before the current
+                // cell is computed, so topology reads never sit on the critical path
+                UpCell cur = nx;
+                int i = pos + gid;
+                if (cur.c < 0) {
+                    nx = load_upcell(corder, cup_off, cup_idx, e + gid, e + gid < e2);
+                } else {
+                    for (;;) {
+                        const int inext = i + ngroups;
+                        const bool more = inext < e;
+                        const UpCell nn = more ? load_upcell(corder, cup_off, cup_idx, inext, true)
+                                               : load_upcell(corder, cup_off, cup_idx, e + gid, e + gid < e2);
+                        accum_upcell<T, G>(cur, cup_idx, g, A, ld, nmonth);
+                        if (!more) { nx = nn; break; }
+                        cur = nn;
+                        i = inext;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                pos = e; e = e2;
+                if (threadIdx.x == 0) *(volatile int *)&s_pos = pos;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -561,7 +668,7 @@ struct wfa_plan {
     // upper forest regrouped by outlet basin (see k_accum_components)
     int comp_level = 0, ncomp = 0, nupper = 0;
     bool comp_ok = false;
-    DevBuf corder, cmask, cnext, comps;
+    DevBuf corder, cmask, cnext, comps, cup_off, cup_idx;
 };
 
 static void plan_free(wfa_plan *p)
@@ -570,7 +677,7 @@ static void plan_free(wfa_plan *p)
     cudaSetDevice(p->device);
     DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
-                      &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps};
+                      &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx};
     for (DevBuf *d : bufs) d->release();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -751,6 +858,23 @@ static int plan_build_components(wfa_plan *p)
     QCK(cudaGetLastError());
     int ncomp = 0;
     QCK(cudaMemcpyAsync(&ncomp, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // CSR of upstream cells: counts -> exclusive scan -> fill
+    QRC(p->cup_off.ensure(((size_t)nu + 1) * 4));
+    k_comp_upcount<<<nb, 256, 0, st>>>(p->cmask.as<uint8_t>(), nu, keys.as<int32_t>());
+    QCK(cudaMemsetAsync(p->cup_off.p, 0, 4, st));
+    {
+        size_t sbytes = 0;
+        QCK(cub::DeviceScan::InclusiveSum(nullptr, sbytes, keys.as<int32_t>(), p->cup_off.as<int32_t>() + 1, nu, st));
+        QRC(temp.ensure(sbytes ? sbytes : 16));
+        QCK(cub::DeviceScan::InclusiveSum(temp.p, sbytes, keys.as<int32_t>(), p->cup_off.as<int32_t>() + 1, nu, st));
+    }
+    int nedges = 0;
+    QCK(cudaMemcpyAsync(&nedges, p->cup_off.as<int32_t>() + nu, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QCK(cudaStreamSynchronize(st));
+    QRC(p->cup_idx.ensure(std::max<size_t>(16, (size_t)nedges * 4)));
+    k_comp_upfill<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(), nu, p->ncol,
+                                      p->cup_off.as<int32_t>(), p->cup_idx.as<int32_t>());
+    QCK(cudaGetLastError());
     QCK(cudaStreamSynchronize(st));
     std::vector<int32_t> beg(ncomp);
     if (ncomp) QCK(cudaMemcpy(beg.data(), cbeg.p, (size_t)ncomp * 4, cudaMemcpyDeviceToHost));
@@ -928,10 +1052,11 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     if (l0 < p->nlevels) {
         if (by_basin) {
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
-            int blocks = std::min(p->ncomp, 148 * 8);
-            k_accum_components<T, G><<<blocks, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(),
-                                                             p->cnext.as<int32_t>(), p->comps.as<int2>(), p->ncomp,
-                                                             p->ticket.as<int>(), p->ncol, A, ld, nmonth);
+            int blocks = std::min(p->ncomp, 148 * 7);
+            k_accum_components<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
+                                                             p->cup_idx.as<int32_t>(), p->cnext.as<int32_t>(),
+                                                             p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(), A, ld,
+                                                             nmonth);
         } else if (!dataflow) {
             k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
                                                    ld, nmonth);

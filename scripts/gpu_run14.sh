@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()"
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/route_bench.py --n 20000 --batches 16,32 --flags 0 2>&1 | grep "{" | tee gpurun_out/route_20000.log
+WFA_COMP_WIDTH=65536 timeout 600 python scripts/route_bench.py --n 20000 --batches 32 --flags 0 2>&1 | grep "{" | tee -a gpurun_out/route_20000.log

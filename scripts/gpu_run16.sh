@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()"
+timeout 1200 python -m pytest tests/test_gpu_wfa.py tests/test_gpu_device_api.py tests/test_gpu_golden.py -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+python scripts/chain_bench.py 2>&1 | grep "{" | grep -E "levels|basin" | tee gpurun_out/chain.log
+timeout 600 python scripts/route_bench.py --n 20000 --batches 32 --flags 0 2>&1 | grep "{" | tee gpurun_out/route_20000.log
