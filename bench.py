@@ -359,13 +359,25 @@ def main():
         basin.close()
         n_e2e = max(1, min(a.steps, 2))
 
+        e2e_parts = {"create_upload_tile_s": 0.0, "objective_s": 0.0, "destroy_s": 0.0}
+
         def e2e_step():
-            with capi.Basin(Pp.numpy(), Ep.numpy(), area, nd, region, 1) as b:
-                r = b.objective_batch(parp.numpy(), qobs, 36, capi.OF_KGE, flags, want_crit=False)
+            t0 = time.perf_counter()
+            b = capi.Basin(Pp.numpy(), Ep.numpy(), area, nd, region, 1)
+            t1 = time.perf_counter()
+            r = b.objective_batch(parp.numpy(), qobs, 36, capi.OF_KGE, flags, want_crit=False)
+            t2 = time.perf_counter()
+            b.close()
+            t3 = time.perf_counter()
+            e2e_parts["create_upload_tile_s"] += t1 - t0
+            e2e_parts["objective_s"] += t2 - t1
+            e2e_parts["destroy_s"] += t3 - t2
             return r["of"]
 
         e2e_step()
         fence()
+        for k_ in e2e_parts:
+            e2e_parts[k_] = 0.0
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             of_e2e = e2e_step()
@@ -379,6 +391,7 @@ def main():
         e2e = {"value": units_step * n_e2e / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(P.nbytes + E.nbytes + area.nbytes + nd.nbytes + region.nbytes + par.nbytes + qobs.nbytes),
                "d2h_bytes_per_step": int(nloc * 8), "steps": n_e2e, "matches_resident_run": same,
+               "seconds_per_step": {k_: v_ / n_e2e for k_, v_ in e2e_parts.items()},
                "api": "gr2m_basin_create + gr2m_objective_batch + gr2m_basin_destroy (pinned host buffers)"}
     else:
         basin.close()

@@ -91,9 +91,9 @@ def _drop_warmup(x, WarmUp):
 
 
 def Run_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters=None, IniState=None,
-                      Save=False, Update=False, flags=0, backend=None):
+                      Save=False, Update=False, flags=0):
     """GR2M for n subbasins.  Returns dict(SINK?, QS, RU, PR, AE, SM, Dates, COMID, EndState)."""
-    be = backend or _capi
+    be = _capi
     t0 = time.perf_counter()
     area = np.asarray(Subbasins.Area, np.float64)
     comid = np.asarray(Subbasins.COMID)
@@ -216,13 +216,13 @@ class _Objective:
 
 def Optim_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters=None, Parameters_Min=None,
                         Parameters_Max=None, Max_Functions=5000, Optimization="NSE", No_Optim=None,
-                        ngs=None, seed=0, flags=0, backend=None, shard=None):
+                        ngs=None, seed=0, flags=0, shard=None):
     """SCE-UA calibration.  Returns dict(Param, Value) rounded as Optim:232-244.
 
     The objective is evaluated for a whole SCE-UA generation at once on the GPU (`ngs` complexes evolve
     in lock-step; see sceua.py); `shard=(rank, world, allgather)` splits each batch across ranks."""
     from .sceua import sceua_batched
-    be = backend or _capi
+    be = _capi
     if Optimization not in _capi.OF_NAMES:
         raise ValueError("Optimization must be 'NSE', 'KGE' or 'RMSE'")
     t0 = time.perf_counter()
@@ -282,12 +282,12 @@ def routing_geometry(Subbasins, Dem):
 
 
 def Routing_GR2MSemiDistr(Model, Subbasins, Dem, AcumIni=None, AcumEnd=None, Save=False, Update=False,
-                          FlowDir=None, flags=0, backend=None):
+                          FlowDir=None, flags=0):
     """Weighted-Flow-Accumulation routing of Model$QS.  Returns dict(QR, Dates, COMID).
 
     `FlowDir` (int16 TauDEM codes) replaces the pitremove + D8Flowdir calls (Routing:88-93) when given;
     otherwise d8prep.fill_and_flowdir derives one from `Dem` on the host (documented deviation)."""
-    be = backend or _capi
+    be = _capi
     t0 = time.perf_counter()
     QS = np.asarray(Model["QS"], np.float64)
     dates = list(Model["Dates"])

@@ -126,6 +126,9 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.fe = par[3 * nreg + reg];
     p.iX1 = 1.0 / p.X1;
     p.i2X1 = 2.0 / p.X1;
+    p.fp10 = p.fp * 10.0;
+    p.fe10 = p.fe * 10.0;
+    p.c01 = 0.1 * p.i2X1;
     p.area = area;
     // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
     p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? 0.499 : -1.0;
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
                 for (int m = 0; m < 8; ++m) {
                     double Pr = sp[m * 64], Er = sp[m * 64 + 32];
                     if (FAST) {
-                        v[m] = p.area * step_fast2(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
+                        v[m] = p.area * step_fast3(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
                     } else {
                         StepOut o = step_literal(p, Pr, Er, S, R, a.f32exp);
                         v[m] = (p.area * o.Q) / tc[m];

@@ -221,6 +221,7 @@ __device__ __forceinline__ double rcbrt_fast(double c)
 // ---- the month step -----------------------------------------------------------------------------
 struct CellPar {
     double X1, X2, iX1, i2X1, fp, fe, area, thr;   // i2X1 = 2/X1; thr: see r_round1
+    double fp10, fe10, c01;                        // 10 fp, 10 fe, 0.1 * 2/X1 (calibration kernel only)
 };
 
 struct StepOut {
@@ -303,6 +304,41 @@ __device__ __forceinline__ double step_fast2(const CellPar &p, double Praw, doub
     S = S2 * y;
     double R2 = p.X2 * (R + (P1 + (S2 - S)));
     double Q = div_fast1(R2 * R2, R2 + 60.0);
+    R = R2 - Q;
+    return Q;
+}
+
+// Calibration-mode step with the forcing correction reduced to its decision: n = rint(10 f x) is the
+// integer R's round() settles on (ties and anything within 1e-3 of one still go through the exact
+// candidate comparison), and the corrected value n/10 is only ever consumed inside 1e-16-tolerant
+// arithmetic here (it is not an output in this mode), so it is formed as n * 0.1 and the exp argument
+// as n * (0.1 * 2/X1) -- same rounding decision, at most one ulp from RN(n/10).
+__device__ __forceinline__ double step_fast3(const CellPar &p, double Praw, double Eraw, double &S, double &R,
+                                             bool f32exp, const double *__restrict__ tab)
+{
+    double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
+    double np_ = (double)__double2int_rn(xp10), ne_ = (double)__double2int_rn(xe10);
+    double fp_ = __dsub_rn(xp10, np_), fe_ = __dsub_rn(xe10, ne_);
+    if (!(fabs(fp_) < p.thr) || !(fabs(fe_) < p.thr)) {   // near a decimal tie (or out of range): exact path
+        np_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fp, Praw)), 10.0);
+        ne_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fe, Eraw)), 10.0);
+    }
+    double Pc = np_ * KC.tenth;
+    double a = exp_tab256(clamp26(np_ * p.c01), tab);
+    double b = exp_tab256(clamp26(ne_ * p.c01), tab);
+    double am = __fma_rn(a, 0.5, -0.5), ap = __fma_rn(a, 0.5, 0.5);
+    double s = S * p.iX1;
+    double S1 = div_fast3(__fma_rn(p.X1, am, S * ap), __fma_rn(s, am, ap));
+    double P1 = (Pc + S) - S1;
+    double bm = __fma_rn(b, 0.5, -0.5), bp = __fma_rn(b, 0.5, 0.5);
+    double S2 = div_fast3(S1, __fma_rn(__fma_rn(S1, -p.iX1, 1.0), bm, bp));
+    double sr = S2 * p.iX1;
+    double c = __fma_rn(sr * sr, sr, 1.0);
+    double y = rcbrt_fast(c);
+    if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
+    S = S2 * y;
+    double R2 = p.X2 * (R + (P1 + (S2 - S)));
+    double Q = div_fast3(R2 * R2, R2 + 60.0);
     R = R2 - Q;
     return Q;
 }

@@ -196,25 +196,6 @@ __device__ __forceinline__ void accum_cell(int32_t c, int g, int ncol, unsigned 
     }
 }
 
-// latency-critical variant for the per-basin / thin sweeps: EVERY upstream row is requested before any
-// addition (up to 9 independent L2 loads in flight), then added in k order.
-template <typename T, int G>
-__device__ __forceinline__ void accum_cell_all(int32_t c, int g, int ncol, unsigned m, T *A, int ld, int nmonth)
-{
-    T *row = A + (size_t)c * ld;
-    for (int j = g; j < nmonth; j += G) {
-        T v[8];
-        T acc = __ldcg(row + j);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (m & (1u << k)) v[k] = __ldcg(up_row(A, c, k + 1, ncol, ld) + j);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (m & (1u << k)) acc += v[k];
-        row[j] = acc;
-    }
-}
-
 // two independent cells of one level interleaved: four loads in flight per lane
 template <typename T, int G, bool CG>
 __device__ __forceinline__ void accum_cell2(int32_t c0, unsigned m0, int32_t c1, unsigned m1, int g, int ncol, T *A,

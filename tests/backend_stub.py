@@ -1,7 +1,7 @@
 """Oracle-backed stand-in for gr2msemidistr_b200.capi, used ONLY by CPU tests of the host-side
 wrappers (date subsetting, parameter tables, rounding, list assembly, SCE-UA, sharding).  It has the
 same Basin / Plan surface as capi but computes with the CPU oracle -- test infrastructure, never a
-product path (the product wrappers default to capi and have no switch that selects this)."""
+product path: the wrappers always call gr2msemidistr_b200.capi; tests swap it with pytest's monkeypatch."""
 import numpy as np
 
 import oracle

@@ -14,6 +14,13 @@ from gr2msemidistr_b200.rround import rround
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+@pytest.fixture(autouse=True)
+def _oracle_backend(monkeypatch):
+    """CPU tests of the wrappers' host logic: swap the ctypes binding for the oracle-backed stub.
+    (The product has no parameter or setting that does this; it is a test-only monkeypatch.)"""
+    monkeypatch.setattr(api, "_capi", backend_stub)
+
+
 @pytest.fixture(scope="module")
 def c1():
     return dict(np.load(os.path.join(G, "c1_inputs.npz"))), dict(np.load(os.path.join(G, "c1_golden.npz")))
@@ -76,7 +83,7 @@ def test_documented_example_has_exact_decimal_ties(c1, oracle):
 def test_run_wrapper_structure_and_rounding(c1, oracle):
     inp, gold = c1
     data, sb = _frame(inp), _subbasins(inp)
-    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=synth.SET0, backend=backend_stub)
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=synth.SET0)
     assert list(m)[:9] == ["SINK", "QS", "RU", "PR", "AE", "SM", "Dates", "COMID", "EndState"]     # Run:256-264
     assert m["QS"].shape == (432, 13) and m["Dates"][0] == dt.date(1981, 1, 1) and m["Dates"][-1] == dt.date(2016, 12, 1)
     for k in ("PR", "AE", "SM", "RU", "QS"):
@@ -85,28 +92,27 @@ def test_run_wrapper_structure_and_rounding(c1, oracle):
     assert np.array_equal(m["SINK"]["obs"], oracle.r_round(inp["qobs"], 3), equal_nan=True)
     assert abs(m["EndState"][4]["Store"]["Prod"] - gold["S_end"][4]) == 0
     # WarmUp drops the first rows of everything (Run:240-251)
-    w = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", WarmUp=36, Parameters=synth.SET0, backend=backend_stub)
+    w = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", WarmUp=36, Parameters=synth.SET0)
     assert w["QS"].shape == (396, 13) and w["Dates"][0] == dt.date(1984, 1, 1)
     assert np.array_equal(w["QS"], m["QS"][36:]) and np.array_equal(w["SINK"]["sim"], m["SINK"]["sim"][36:])
     # a sub-period, then EndState -> IniState continues the run exactly (Run:151-179)
-    a = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1999", Parameters=synth.SET0, backend=backend_stub)
-    b = api.Run_GR2MSemiDistr(data, sb, "01/2000", "12/2016", Parameters=synth.SET0, IniState=a["EndState"],
-                              backend=backend_stub)
+    a = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1999", Parameters=synth.SET0)
+    b = api.Run_GR2MSemiDistr(data, sb, "01/2000", "12/2016", Parameters=synth.SET0, IniState=a["EndState"])
     assert np.array_equal(np.vstack([a["QS"], b["QS"]]), m["QS"])
     # without Q there is no SINK (Run:268-277); bad dates and parameter counts are rejected
-    noq = api.Run_GR2MSemiDistr(data.drop(columns="Q"), sb, "01/1981", "12/1981", Parameters=synth.SET0, backend=backend_stub)
+    noq = api.Run_GR2MSemiDistr(data.drop(columns="Q"), sb, "01/1981", "12/1981", Parameters=synth.SET0)
     assert "SINK" not in noq and noq["PR"].shape == (12, 13)
     with pytest.raises(ValueError):
-        api.Run_GR2MSemiDistr(data, sb, "01/1975", "12/2016", Parameters=synth.SET0, backend=backend_stub)
+        api.Run_GR2MSemiDistr(data, sb, "01/1975", "12/2016", Parameters=synth.SET0)
     with pytest.raises(ValueError):
-        api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=[1, 2, 3], backend=backend_stub)
+        api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", Parameters=[1, 2, 3])
 
 
 def test_run_wrapper_single_subbasin_branch(c1, oracle):
     inp, _ = c1
     data = _frame(inp).iloc[:, [0, 3, 16, 27]]            # DatesR, P_3, E_3, Q
     sb = gis.Subbasins(inp["area"][2:3], np.array(["A"]), inp["comid"][2:3], [])
-    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1990", Parameters=synth.SET0, backend=backend_stub)
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/1990", Parameters=synth.SET0)
     sim = oracle.run(inp["P"][2:3, :120], inp["E"][2:3, :120], inp["area"][2:3], inp["ndays"][:120], np.zeros(1, np.int32), 1, synth.SET0)
     ru = oracle.r_round(sim["RU"][0], 1)
     qs = oracle.r_round(inp["area"][2] * ru / (86.4 * inp["ndays"][:120]), 1)      # Run:195-200 uses the rounded ru
@@ -117,7 +123,7 @@ def test_save_and_update_files(c1, tmp_path, monkeypatch):
     inp, _ = c1
     data, sb = _frame(inp), _subbasins(inp)
     monkeypatch.chdir(tmp_path)
-    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "03/1981", Parameters=synth.SET0, Save=True, backend=backend_stub)
+    m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "03/1981", Parameters=synth.SET0, Save=True)
     f = tmp_path / "Outputs" / "PR_GR2MSemiDistr_198103.txt"                      # Run:318-322
     names, dates, mat = api._read_table(str(f))
     assert names == [f"PR_{c}" for c in inp["comid"]] and dates == m["Dates"] and np.array_equal(mat, m["PR"])
@@ -126,7 +132,7 @@ def test_save_and_update_files(c1, tmp_path, monkeypatch):
     os.rename(f, tmp_path / "Outputs" / "PR_GR2MSemiDistr_198104.txt")
     for k in ("AE", "SM", "RU"):
         os.rename(tmp_path / "Outputs" / f"{k}_GR2MSemiDistr_198103.txt", tmp_path / "Outputs" / f"{k}_GR2MSemiDistr_198104.txt")
-    nxt = api.Run_GR2MSemiDistr(data, sb, "04/1981", "04/1981", Parameters=synth.SET0, IniState=m["EndState"], backend=backend_stub)
+    nxt = api.Run_GR2MSemiDistr(data, sb, "04/1981", "04/1981", Parameters=synth.SET0, IniState=m["EndState"])
     api._save_run(nxt, "04/1981", True, outdir=str(tmp_path / "Outputs"), today=today)
     names, dates, mat = api._read_table(str(tmp_path / "Outputs" / "PR_GR2MSemiDistr_198105.txt"))
     assert len(dates) == 4 and np.array_equal(mat[3], nxt["PR"][0]) and not (tmp_path / "Outputs" / "PR_GR2MSemiDistr_198104.txt").exists()
@@ -139,10 +145,10 @@ def test_routing_wrapper(c1, oracle):
     src, off, cells = api.routing_geometry(sb, dem)
     assert np.array_equal(src, inp["src_cell"]) and np.array_equal(off, inp["poly_off"]) and np.array_equal(cells, inp["poly_cells"])
     model = {"QS": oracle.r_round(gold["QS"].T, 1), "Dates": [dt.date(1981 + t // 12, t % 12 + 1, 1) for t in range(432)]}
-    r = api.Routing_GR2MSemiDistr(model, sb, dem, backend=backend_stub)           # derives FlowDir from the DEM
+    r = api.Routing_GR2MSemiDistr(model, sb, dem)           # derives FlowDir from the DEM
     assert list(r)[:3] == ["QR", "Dates", "COMID"] and r["QR"].shape == (432, 13)
     assert np.array_equal(r["QR"], oracle.r_round(gold["QR"].T, 1))
-    sub = api.Routing_GR2MSemiDistr(model, sb, dem, AcumIni="01/1990", AcumEnd="12/1990", FlowDir=inp["flowdir"], backend=backend_stub)
+    sub = api.Routing_GR2MSemiDistr(model, sb, dem, AcumIni="01/1990", AcumEnd="12/1990", FlowDir=inp["flowdir"])
     assert sub["QR"].shape == (12, 13) and np.array_equal(sub["QR"], r["QR"][108:120]) and sub["Dates"][0] == dt.date(1990, 1, 1)
     # a routed discharge is at least the subbasin's own contribution when its source cell is interior and clean
     assert np.all(r["QR"].max(axis=1) >= model["QS"].max(axis=1) - 0.05)
@@ -153,7 +159,7 @@ def test_optim_wrapper_with_stub_backend(c1):
     data, sb = _frame(inp), _subbasins(inp)
     res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=400, Optimization="KGE", ngs=4, backend=backend_stub)
+                                  Max_Functions=400, Optimization="KGE", ngs=4)
     assert res["Param"].shape == (4,) and np.array_equal(res["Param"], rround(res["Param"], 3))
     assert np.all(res["Param"] >= [1, 0.01, 0.8, 0.8]) and np.all(res["Param"] <= [2000, 2, 1.2, 1.2])
     with backend_stub.Basin(inp["P"][:, :264], inp["E"][:, :264], inp["area"], inp["ndays"][:264], np.zeros(13, np.int32), 1) as b:
@@ -181,6 +187,6 @@ def test_optim_fixed_regions_are_spliced_back(oracle):
     start = np.array([1000.0, 800.0, 1.0, 1.1, 1.0, 0.9, 1.0, 1.05])
     res = api.Optim_GR2MSemiDistr(pd.DataFrame(cols), sb, "01/1981", "12/1985", WarmUp=12, Parameters=start,
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=1500, Optimization="RMSE", No_Optim=["B"], ngs=6, backend=backend_stub)
+                                  Max_Functions=1500, Optimization="RMSE", No_Optim=["B"], ngs=6)
     assert np.array_equal(res["Param"][[1, 3, 5, 7]], truth[[1, 3, 5, 7]])
     assert res["Value"] < 5.0

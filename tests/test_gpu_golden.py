@@ -75,18 +75,24 @@ def test_c2_objective_against_golden(capi, c1):
         assert np.max(np.abs(r[w]["of"] - gold["of"][:, w])) <= 1e-3 + 1e-9
 
 
-def test_wrappers_on_the_gpu_match_the_oracle_backend(capi, c1):
+def _with_stub(monkeypatch, fn, *a, **k):
+    with monkeypatch.context() as mp:
+        mp.setattr(api, "_capi", backend_stub)
+        return fn(*a, **k)
+
+
+def test_wrappers_on_the_gpu_match_the_oracle_backend(capi, c1, monkeypatch):
     inp, gold = c1
     data, sb = _frame(inp), _subbasins(inp)
     dem = gis.Raster(np.where(inp["dem"] == -32768, -3e38, inp["dem"]).astype(np.float32)[None], *inp["dem_geo"], nodata=-3e38)
     m = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", WarmUp=12, Parameters=synth.SET0)
-    ref = api.Run_GR2MSemiDistr(data, sb, "01/1981", "12/2016", WarmUp=12, Parameters=synth.SET0, backend=backend_stub)
+    ref = _with_stub(monkeypatch, api.Run_GR2MSemiDistr, data, sb, "01/1981", "12/2016", WarmUp=12, Parameters=synth.SET0)
     for k in ("PR", "AE", "SM", "RU", "QS"):
         d = np.abs(m[k] - ref[k])
         assert d.max() <= 0.1 + 1e-9 and np.mean(d > 0) < 1e-4, k        # identical unless a value sits on a rounding tie
     assert np.max(np.abs(m["SINK"]["sim"] - ref["SINK"]["sim"])) <= 0.1 + 1e-9
     r = api.Routing_GR2MSemiDistr(m, sb, dem, FlowDir=inp["flowdir"])
-    rr = api.Routing_GR2MSemiDistr(ref, sb, dem, FlowDir=inp["flowdir"], backend=backend_stub)
+    rr = _with_stub(monkeypatch, api.Routing_GR2MSemiDistr, ref, sb, dem, FlowDir=inp["flowdir"])
     assert r["QR"].shape == (420, 13) and np.max(np.abs(r["QR"] - rr["QR"])) <= 0.1 + 1e-9
     # month-by-month update workflow: one month from the saved state (Run:138-142, 151-179)
     a = api.Run_GR2MSemiDistr(data, sb, "01/1981", "11/2016", Parameters=synth.SET0)
@@ -97,7 +103,7 @@ def test_wrappers_on_the_gpu_match_the_oracle_backend(capi, c1):
     assert r1["QR"].shape == (1, 13)
 
 
-def test_calibration_on_the_gpu(capi, c1):
+def test_calibration_on_the_gpu(capi, c1, monkeypatch):
     inp, _ = c1
     data, sb = _frame(inp), _subbasins(inp)
     res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
@@ -105,8 +111,8 @@ def test_calibration_on_the_gpu(capi, c1):
                                   Max_Functions=20000, Optimization="KGE", ngs=128)
     # same search with the oracle evaluating the objective: identical trajectory unless an objective
     # value differs in its third decimal, so the optimum agrees to the quantisation of Optim:210
-    ref = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
-                                  Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=3000, Optimization="KGE", ngs=16, backend=backend_stub)
+    ref = _with_stub(monkeypatch, api.Optim_GR2MSemiDistr, data, sb, "01/1981", "12/2002", WarmUp=36,
+                     Parameters=[1000, 1, 1, 1], Parameters_Min=[1, 0.01, 0.8, 0.8],
+                     Parameters_Max=[2000, 2, 1.2, 1.2], Max_Functions=3000, Optimization="KGE", ngs=16)
     assert res["Value"] >= ref["Value"] - 0.02 and res["Value"] > 0.5
     assert res["evaluations"] > 5000          # whole generations of 128 complexes x 9 points per batch
