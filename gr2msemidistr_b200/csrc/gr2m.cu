@@ -67,10 +67,8 @@ extern "C" int gr2m_set_device(int device)
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-constexpr int TM = 16;    // months per shared-memory stage
-constexpr int NST = 3;    // stages in flight
+constexpr int TM = 16;    // the forcing table is padded to a multiple of this many months
 constexpr int SPB = 8;    // parameter sets (warps) per block
-constexpr int STAGE_DBL = TM * 64;
 
 // raw [ncell][ntime] (R column-major) -> tiled month-major F[tile][t][var][32]
 __global__ void k_tile_forcing(const double *__restrict__ P, const double *__restrict__ E, int ncell, int ntime,
@@ -172,86 +170,7 @@ struct CalibArgs {
 // sum_c QS[t, c] per (set, month) leave the SM (Optim:186-196).  Block = SPB sets x (a range of cell
 // tiles processed one after another); forcing stages arrive by bulk async copy and are reused by
 // all SPB sets; per-set outlet accumulators live in shared memory across the tile loop.
-template <bool FAST>
-__global__ void __launch_bounds__(SPB * 32, 3) k_gr2m_calib(CalibArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);   // NST * STAGE_DBL
-    double *qacc = stage + NST * STAGE_DBL;                 // SPB * ntime_pad
-    double *tconv = qacc + SPB * a.ntime_pad;               // ntime_pad
-    double *tab = tconv + a.ntime_pad;                      // 32
-    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 32);   // NST
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
-    const int set = sg * SPB + warp;
-    const bool set_ok = set < a.nsets;
-    const int tile0 = cs * a.tiles_per_split;
-    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
-    const int nchunk = a.ntime_pad / TM;
-    const int total = (tile1 - tile0) * nchunk;
-
-    for (int i = tid; i < SPB * a.ntime_pad; i += blockDim.x) qacc[i] = 0.0;
-    for (int i = tid; i < a.ntime_pad; i += blockDim.x) tconv[i] = i < a.ntime ? a.tconv[i] : 1.0;
-    if (tid < 32) tab[tid] = c_exp2_tab[tid];
-    if (tid == 0) {
-        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;   // stages of consecutive tiles are contiguous
-    if (tid == 0) {
-        for (int g = 0; g < NST - 1 && g < total; ++g) {
-            mbar_arrive_expect_tx(&full[g], STAGE_DBL * 8);
-            bulk_g2s(stage + g * STAGE_DBL, Fbase + (size_t)g * STAGE_DBL, STAGE_DBL * 8, &full[g]);
-        }
-    }
-
-    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4 * a.nreg;
-    int g = 0;
-    for (int tile = tile0; tile < tile1; ++tile) {
-        const int cell = tile * 32 + lane;
-        const bool cell_ok = cell < a.ncell;
-        CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0, a.forcing_ok);
-        double S = 0.3 * p.X1, R = 0.5 * p.X2;   // airGR default IniResLevels (Optim never passes IniState)
-        for (int ch = 0; ch < nchunk; ++ch, ++g) {
-            if (tid == 0 && g + NST - 1 < total) {
-                int gn = g + NST - 1, sn = gn % NST;
-                mbar_arrive_expect_tx(&full[sn], STAGE_DBL * 8);
-                bulk_g2s(stage + sn * STAGE_DBL, Fbase + (size_t)gn * STAGE_DBL, STAGE_DBL * 8, &full[sn]);
-            }
-            mbar_wait(&full[g % NST], (g / NST) & 1);
-            if (set_ok) {
-                const double *sp = stage + (g % NST) * STAGE_DBL;
-#pragma unroll 1
-                for (int h = 0; h < TM / 8; ++h) {
-                    double v[8];
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const int mm = h * 8 + m, t = ch * TM + mm;
-                        double Pr = sp[mm * 64 + lane], Er = sp[mm * 64 + 32 + lane];
-                        StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab)
-                                         : step_literal(p, Pr, Er, S, R, a.f32exp);
-                        v[m] = FAST ? (p.area * o.Q) * tconv[t] : (p.area * o.Q) / tconv[t];
-                    }
-                    double s = warp_reduce8(v, lane);
-                    if ((lane & 3) == 0) {
-                        int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                        qacc[warp * a.ntime_pad + ch * TM + h * 8 + idx] += s;
-                    }
-                }
-            }
-            __syncthreads();   // stage g%NST is free again (refilled by the copy issued next iteration)
-        }
-    }
-    if (set_ok)
-        for (int t = lane; t < a.ntime; t += 32)
-            a.partial[((size_t)cs * a.nsets + set) * a.ntime + t] = qacc[warp * a.ntime_pad + t];
-}
-
-// Variant 2 of the same kernel, tuned for occupancy and for warps that drift apart:
-//  * 8-month stages (4 KiB), 4 in flight  -> 51 KiB shared memory per CTA, 4 CTAs (32 warps) per SM;
+//  * 8-month stages (4 KiB), 4 in flight  -> 53 KiB shared memory per CTA, 4 CTAs (32 warps) per SM;
 //  * no block barrier in the month loop: every warp counts itself out of a stage and the LAST warp
 //    to leave a stage re-arms its mbarrier and issues the bulk copy that refills it, so fast warps
 //    run up to 3 stages ahead of slow ones instead of meeting them every stage.
@@ -741,16 +660,9 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
     a.forcing_ok = b->forcing_ok;
-    static int variant = -1;   // GR2M_CALIB_VARIANT=1 selects the first kernel (development A/B switch)
-    if (variant < 0) {
-        const char *ev = getenv("GR2M_CALIB_VARIANT");
-        variant = ev ? atoi(ev) : 2;
-    }
-    const bool v2 = variant != 1;
-    size_t smem = v2 ? (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 256) * sizeof(double) + NST2 * 12
-                     : (size_t)(NST * STAGE_DBL + SPB * b->ntime_pad + b->ntime_pad + 32) * sizeof(double) + NST * 8;
+    size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 256) * sizeof(double) + NST2 * 12;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
-    auto kern = v2 ? (fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>) : (fast ? k_gr2m_calib<true> : k_gr2m_calib<false>);
+    auto kern = fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, b->stream));
     kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);

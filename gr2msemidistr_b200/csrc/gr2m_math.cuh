@@ -1,12 +1,15 @@
 // gr2m_math.cuh -- FP64 device arithmetic of the GR2M step (sm_100a).
 //
-// Two formulations of the same month step (airGR frun_GR2M.f90 MOD_GR2M, reached
+// Three formulations of the same month step (airGR frun_GR2M.f90 MOD_GR2M, reached
 // from R/Run_GR2MSemiDistr.R:181-184 and R/Optim_GR2MSemiDistr.R:174-177):
 //   step_literal : IEEE division, libdevice exp()/pow(), operation order as written in airGR.
 //   step_fast    : same algebra with the two tanh divisions folded into the store updates
 //                  (3 divisions instead of 12), a table-driven exp, a Halley-refined reciprocal cube
-//                  root and Newton-refined MUFU reciprocals.  Every building block is accurate to
-//                  ~1 ulp, so the two agree to ~1e-14 relative; tests hold both to 1e-10.
+//                  root and Newton-refined MUFU reciprocals; returns every series (simulation mode).
+//   step_fast3   : calibration mode (only Q leaves the thread): additionally a 256-entry exp table,
+//                  halved tanh terms, rint by the conversion unit, one division step less.
+// Every building block is accurate to 1-2 ulp, so they agree to ~1e-14 relative; tests hold all
+// of them to 1e-10 against the CPU oracle.
 // The forcing correction round(f*x, 1) (R/Run_GR2MSemiDistr.R:101-102) is BIT-EXACT in both: a wrong
 // rounding decision is a 0.1 mm error, not an ulp.
 #pragma once
@@ -268,44 +271,6 @@ __device__ __forceinline__ StepOut step_fast(const CellPar &p, double Praw, doub
     o.Pc = Pc;
     o.Q = Q;
     return o;
-}
-
-// Leaner formulation used by the calibration kernel (bit-level differences from step_fast are at the
-// ulp level): 256-entry exp table, conversion-unit rint in the forcing correction, halved
-// tanh terms (ah = (a-1)/2 etc. via FMA with immediates, which removes the S1+S1 add), one division
-// step less.  Returns Q only; `tab` is the 256-entry table.
-__device__ __forceinline__ double step_fast2(const CellPar &p, double Praw, double Eraw, double &S, double &R,
-                                             bool f32exp, const double *__restrict__ tab)
-{
-    // forcing correction for P and E together: one tie test and one (rare) branch per month
-    double xp = __dmul_rn(p.fp, Praw), xe = __dmul_rn(p.fe, Eraw);
-    double xp10 = __dmul_rn(xp, 10.0), xe10 = __dmul_rn(xe, 10.0);
-    double np_ = (double)__double2int_rn(xp10), ne_ = (double)__double2int_rn(xe10);
-    double fp_ = __dsub_rn(xp10, np_), fe_ = __dsub_rn(xe10, ne_);
-    double Pc = div10_rn(np_), Ec = div10_rn(ne_);
-    if (!(fabs(fp_) < p.thr) || !(fabs(fe_) < p.thr)) {
-        Pc = r_round1_exact(xp);
-        Ec = r_round1_exact(xe);
-    }
-    double a = exp_tab256(clamp26(Pc * p.i2X1), tab);
-    double b = exp_tab256(clamp26(Ec * p.i2X1), tab);
-    // S1 = (S (a+1) + X1 (a-1)) / ((a+1) + s (a-1)), numerator and denominator both halved
-    double am = __fma_rn(a, 0.5, -0.5), ap = __fma_rn(a, 0.5, 0.5);
-    double s = S * p.iX1;
-    double S1 = div_fast1(__fma_rn(p.X1, am, S * ap), __fma_rn(s, am, ap));
-    double P1 = (Pc + S) - S1;
-    // S2 = 2 S1 / ((b+1) + (1 - S1/X1)(b-1)) = S1 / ((b+1)/2 + (1 - S1/X1)(b-1)/2)
-    double bm = __fma_rn(b, 0.5, -0.5), bp = __fma_rn(b, 0.5, 0.5);
-    double S2 = div_fast1(S1, __fma_rn(__fma_rn(S1, -p.iX1, 1.0), bm, bp));
-    double sr = S2 * p.iX1;
-    double c = __fma_rn(sr * sr, sr, 1.0);
-    double y = rcbrt_fast(c);
-    if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
-    S = S2 * y;
-    double R2 = p.X2 * (R + (P1 + (S2 - S)));
-    double Q = div_fast1(R2 * R2, R2 + 60.0);
-    R = R2 - Q;
-    return Q;
 }
 
 // Calibration-mode step with the forcing correction reduced to its decision: n = rint(10 f x) is the
