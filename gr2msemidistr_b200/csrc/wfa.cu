@@ -343,18 +343,26 @@ __global__ void k_comp_upcount(const uint8_t *__restrict__ cmask, int nu, int32_
     if (i < nu) cnt[i] = __popc(cmask[i]);
 }
 
+// bit 31 of an entry marks a "fresh" upstream cell: one level below c, i.e. written in the level
+// immediately before c's -- the only rows that sit on the sweep's latency chain
+constexpr uint32_t UP_FRESH = 0x80000000u;
+constexpr uint32_t UP_ID = 0x7fffffffu;
+
 __global__ void k_comp_upfill(const int32_t *__restrict__ corder, const uint8_t *__restrict__ cmask, int nu, int ncol,
-                              const int32_t *__restrict__ cup_off, int32_t *__restrict__ cup_idx)
+                              const int32_t *__restrict__ level, const int32_t *__restrict__ cup_off,
+                              uint32_t *__restrict__ cup_idx)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nu) return;
     int32_t c = corder[i];
+    const int lc = level[c];
     unsigned m = cmask[i];
     int q = cup_off[i];
     while (m) {
         int k = __ffs(m);
         m &= m - 1;
-        cup_idx[q++] = c + c_dy[k] * ncol + c_dx[k];
+        int32_t u = c + c_dy[k] * ncol + c_dx[k];
+        cup_idx[q++] = (uint32_t)u | (level[u] == lc - 1 ? UP_FRESH : 0u);
     }
 }
 
@@ -376,12 +384,13 @@ __global__ void k_comp_next(const uint8_t *__restrict__ lstart, int nu, int32_t 
 // the same list and pulls every row the sweep will touch into L2.
 constexpr int PF_AHEAD = 384;
 
-struct UpCell {           // first cell of a lane group in a level, with up to 3 upstream ids preloaded
-    int32_t c, b, n, u0, u1, u2;
+struct UpCell {           // a cell with up to 3 upstream ids (k order) preloaded; bit 31 of an id = fresh
+    int32_t c, b, n;
+    uint32_t u0, u1, u2;
 };
 
 __device__ __forceinline__ UpCell load_upcell(const int32_t *__restrict__ corder, const int32_t *__restrict__ cup_off,
-                                              const int32_t *__restrict__ cup_idx, int i, bool valid)
+                                              const uint32_t *__restrict__ cup_idx, int i, bool valid)
 {
     UpCell x;
     x.c = -1; x.b = 0; x.n = 0; x.u0 = x.u1 = x.u2 = 0;
@@ -397,11 +406,12 @@ __device__ __forceinline__ UpCell load_upcell(const int32_t *__restrict__ corder
 }
 
 template <typename T, int G>
-__device__ __forceinline__ void accum_upcell(const UpCell &x, const int32_t *__restrict__ cup_idx, int g, T *A, int ld,
+__device__ __forceinline__ void accum_upcell(const UpCell &x, const uint32_t *__restrict__ cup_idx, int g, T *A, int ld,
                                              int nmonth)
 {
     T *row = A + (size_t)x.c * ld;
-    const T *r0 = A + (size_t)x.u0 * ld, *r1 = A + (size_t)x.u1 * ld, *r2 = A + (size_t)x.u2 * ld;
+    const T *r0 = A + (size_t)(x.u0 & UP_ID) * ld, *r1 = A + (size_t)(x.u1 & UP_ID) * ld,
+            *r2 = A + (size_t)(x.u2 & UP_ID) * ld;
     for (int j = g; j < nmonth; j += G) {
         T own = __ldcg(row + j), a0 = __ldcg(r0 + j), a1 = 0, a2 = 0;
         if (x.n > 1) a1 = __ldcg(r1 + j);
@@ -409,7 +419,7 @@ __device__ __forceinline__ void accum_upcell(const UpCell &x, const int32_t *__r
         T acc = own + a0;
         if (x.n > 1) acc += a1;
         if (x.n > 2) acc += a2;
-        for (int q = 3; q < x.n; ++q) acc += __ldcg(A + (size_t)cup_idx[x.b + q] * ld + j);
+        for (int q = 3; q < x.n; ++q) acc += __ldcg(A + (size_t)(cup_idx[x.b + q] & UP_ID) * ld + j);
         row[j] = acc;
     }
 }
@@ -417,7 +427,7 @@ __device__ __forceinline__ void accum_upcell(const UpCell &x, const int32_t *__r
 template <typename T, int G>
 __global__ void __launch_bounds__(288) k_accum_components(const int32_t *__restrict__ corder,
                                                           const int32_t *__restrict__ cup_off,
-                                                          const int32_t *__restrict__ cup_idx,
+                                                          const uint32_t *__restrict__ cup_idx,
                                                           const int32_t *__restrict__ cnext,
                                                           const int2 *__restrict__ comps, int ncomp, int *ticket,
                                                           T *A, int ld, int nmonth)
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(288) k_accum_components(const int32_t *__restr
                 const char *r = reinterpret_cast<const char *>(A + (size_t)corder[i] * ld);
                 for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + bb));
                 for (int q = cup_off[i]; q < cup_off[i + 1]; ++q) {
-                    const char *u = reinterpret_cast<const char *>(A + (size_t)cup_idx[q] * ld);
+                    const char *u = reinterpret_cast<const char *>(A + (size_t)(cup_idx[q] & UP_ID) * ld);
                     for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + bb));
                 }
             }
@@ -473,6 +483,110 @@ __global__ void __launch_bounds__(288) k_accum_components(const int32_t *__restr
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 pos = e; e = e2;
+                if (threadIdx.x == 0) *(volatile int *)&s_pos = pos;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Same walk for nmonth <= G (every lane owns exactly one month): the chain is taken off the memory
+// system.  Each lane group (a) keeps the values of its first cell of the NEXT level in registers --
+// own weight and every upstream value that is already final (not fresh) are requested one level
+// ahead -- and (b) publishes the row it has just produced in a shared-memory slot tagged with the
+// cell id, where the next level finds its fresh upstream rows.  What is left on the critical path of
+// a level is a barrier, a tag search, a shared-memory read and an add.
+template <typename T, int G>
+__global__ void __launch_bounds__(288) k_accum_components_fw(const int32_t *__restrict__ corder,
+                                                             const int32_t *__restrict__ cup_off,
+                                                             const uint32_t *__restrict__ cup_idx,
+                                                             const int32_t *__restrict__ cnext,
+                                                             const int2 *__restrict__ comps, int ncomp, int *ticket,
+                                                             T *A, int ld, int nmonth)
+{
+    constexpr int NG = 256 / G;
+    __shared__ int s_k, s_pos;
+    __shared__ int32_t fw_cell[2][NG];
+    __shared__ T fw_row[2][NG][G];
+    const int gid = threadIdx.x / G, g = threadIdx.x % G;
+    const bool prefetcher = threadIdx.x >= 256;
+    const bool live = g < nmonth;
+    const int lane = threadIdx.x & 31;
+    const int row_bytes = nmonth * (int)sizeof(T);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_k = atomicAdd(ticket, 1);
+            s_pos = s_k < ncomp ? comps[s_k].x : 0;
+        }
+        if (threadIdx.x < 2 * NG) (&fw_cell[0][0])[threadIdx.x] = -1;
+        __syncthreads();
+        const int k = s_k;
+        if (k >= ncomp) return;
+        int pos = comps[k].x;
+        const int ce = comps[k].y;
+        if (prefetcher) {
+            for (int i = pos + lane; i < ce; i += 32) {
+                while (i > *(volatile int *)&s_pos + PF_AHEAD) __nanosleep(64);
+                const char *r = reinterpret_cast<const char *>(A + (size_t)corder[i] * ld);
+                for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + bb));
+                for (int q = cup_off[i]; q < cup_off[i + 1]; ++q) {
+                    const char *u = reinterpret_cast<const char *>(A + (size_t)(cup_idx[q] & UP_ID) * ld);
+                    for (int bb = 0; bb < row_bytes; bb += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + bb));
+                }
+            }
+        } else {
+            int e = cnext[pos], par = 0;
+            UpCell nx = load_upcell(corder, cup_off, cup_idx, pos + gid, pos + gid < e);
+            T pown = 0, pv0 = 0, pv1 = 0, pv2 = 0;       // values of nx requested ahead (final ones only)
+            if (nx.c >= 0 && live) {
+                pown = __ldcg(A + (size_t)nx.c * ld + g);
+                if (!(nx.u0 & UP_FRESH)) pv0 = __ldcg(A + (size_t)(nx.u0 & UP_ID) * ld + g);
+                if (nx.n > 1 && !(nx.u1 & UP_FRESH)) pv1 = __ldcg(A + (size_t)(nx.u1 & UP_ID) * ld + g);
+                if (nx.n > 2 && !(nx.u2 & UP_FRESH)) pv2 = __ldcg(A + (size_t)(nx.u2 & UP_ID) * ld + g);
+            }
+            while (pos < ce) {
+                const int e2 = e < ce ? cnext[e] : ce;
+                const UpCell cur = nx;
+                const T own = pown, v0 = pv0, v1 = pv1, v2 = pv2;
+                // ids of this group's first cell of the next level (values follow after this level's work)
+                nx = load_upcell(corder, cup_off, cup_idx, e + gid, e + gid < e2);
+                const int32_t *tags = fw_cell[par ^ 1];
+                if (cur.c >= 0) {
+                    // fresh upstream rows: shared-memory slot of the previous level if one holds them
+                    auto fetch = [&](uint32_t u, T ahead) -> T {
+                        if (!(u & UP_FRESH)) return ahead;
+                        const int32_t id = (int32_t)(u & UP_ID);
+                        int slot = -1;
+#pragma unroll
+                        for (int q = 0; q < NG; ++q)
+                            if (tags[q] == id) slot = q;
+                        if (slot >= 0) return fw_row[par ^ 1][slot][g];
+                        return live ? __ldcg(A + (size_t)id * ld + g) : (T)0;
+                    };
+                    T acc = own + fetch(cur.u0, v0);
+                    if (cur.n > 1) acc += fetch(cur.u1, v1);
+                    if (cur.n > 2) acc += fetch(cur.u2, v2);
+                    for (int q = 3; q < cur.n; ++q) {
+                        const uint32_t u = cup_idx[cur.b + q];
+                        acc += fetch(u, live && !(u & UP_FRESH) ? __ldcg(A + (size_t)(u & UP_ID) * ld + g) : (T)0);
+                    }
+                    if (live) A[(size_t)cur.c * ld + g] = acc;
+                    fw_row[par][gid][g] = acc;
+                }
+                if (g == 0) fw_cell[par][gid] = cur.c;
+                // remaining cells of this level (only when it is wider than the CTA has lane groups)
+                for (int i = pos + gid + NG; i < e; i += NG)
+                    accum_upcell<T, G>(load_upcell(corder, cup_off, cup_idx, i, true), cup_idx, g, A, ld, nmonth);
+                // request next level's final values now; they land while the barrier is crossed
+                pown = pv0 = pv1 = pv2 = 0;
+                if (nx.c >= 0 && live) {
+                    pown = __ldcg(A + (size_t)nx.c * ld + g);
+                    if (!(nx.u0 & UP_FRESH)) pv0 = __ldcg(A + (size_t)(nx.u0 & UP_ID) * ld + g);
+                    if (nx.n > 1 && !(nx.u1 & UP_FRESH)) pv1 = __ldcg(A + (size_t)(nx.u1 & UP_ID) * ld + g);
+                    if (nx.n > 2 && !(nx.u2 & UP_FRESH)) pv2 = __ldcg(A + (size_t)(nx.u2 & UP_ID) * ld + g);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                pos = e; e = e2; par ^= 1;
                 if (threadIdx.x == 0) *(volatile int *)&s_pos = pos;
             }
         }
@@ -854,7 +968,7 @@ static int plan_build_components(wfa_plan *p)
     QCK(cudaStreamSynchronize(st));
     QRC(p->cup_idx.ensure(std::max<size_t>(16, (size_t)nedges * 4)));
     k_comp_upfill<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(), nu, p->ncol,
-                                      p->cup_off.as<int32_t>(), p->cup_idx.as<int32_t>());
+                                      p->level.as<int32_t>(), p->cup_off.as<int32_t>(), p->cup_idx.as<uint32_t>());
     QCK(cudaGetLastError());
     QCK(cudaStreamSynchronize(st));
     std::vector<int32_t> beg(ncomp);
@@ -1034,10 +1148,16 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
         if (by_basin) {
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
             int blocks = std::min(p->ncomp, 148 * 7);
-            k_accum_components<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
-                                                             p->cup_idx.as<int32_t>(), p->cnext.as<int32_t>(),
-                                                             p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(), A, ld,
-                                                             nmonth);
+            if (G >= 16 && nmonth <= G && !(flags & WFA_NO_FORWARD))
+                k_accum_components_fw<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
+                                                                    p->cup_idx.as<uint32_t>(), p->cnext.as<int32_t>(),
+                                                                    p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(),
+                                                                    A, ld, nmonth);
+            else
+                k_accum_components<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
+                                                                 p->cup_idx.as<uint32_t>(), p->cnext.as<int32_t>(),
+                                                                 p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(), A,
+                                                                 ld, nmonth);
         } else if (!dataflow) {
             k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
                                                    ld, nmonth);

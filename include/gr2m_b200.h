@@ -57,6 +57,7 @@ extern "C" {
 #define WFA_LEVEL_SYNC        4   /* sweep the upper levels grid-wide (one launch / one CTA per level) instead of
                                      per outlet basin, which is the default when the forest splits well */
 #define WFA_DATAFLOW          8   /* flag-driven dataflow kernel for the thin tail instead */
+#define WFA_NO_FORWARD        16   /* per-basin sweep without shared-memory forwarding of fresh rows (A/B switch) */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
 typedef struct wfa_plan   wfa_plan;     /* D8 topology plan resident in HBM */

@@ -23,7 +23,7 @@ info = plan.basin_info()
 print(json.dumps({"levels": plan.nlevels, "cells": plan.norder, "basins": info}))
 for ld in (32, 8):
     A = torch.rand((d.size, ld), dtype=torch.float64, device=dev)
-    for fl, name in ((0, "basin"), (4, "levelsync"), (8, "dataflow")):
+    for fl, name in ((0, "basin+forward"), (16, "basin"), (4, "levelsync")):
         best = 1e9
         for _ in range(3):
             A.uniform_(0, 1)

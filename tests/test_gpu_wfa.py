@@ -151,7 +151,15 @@ def test_per_basin_sweep_is_used_and_bit_identical(capi, oracle, rng):
         assert info["enabled"] and info["nbasins"] >= 32 and info["nupper"] > 0
         A = p.accumulate(W, capi.WFA_NO_CONTAMINATION)
         B = p.accumulate(W, capi.WFA_NO_CONTAMINATION | capi.WFA_LEVEL_SYNC)
+        # 32 and 20 months take the shared-memory-forwarding kernel (nmonth <= lanes per cell), 33 the general one
+        C32 = p.accumulate(W[:32], capi.WFA_NO_CONTAMINATION)
+        D32 = p.accumulate(W[:32], capi.WFA_NO_CONTAMINATION | capi.WFA_NO_FORWARD)
+        C20 = p.accumulate(W[:20], capi.WFA_NO_CONTAMINATION | capi.WFA_F32)
+        D20 = p.accumulate(W[:20], capi.WFA_NO_CONTAMINATION | capi.WFA_F32 | capi.WFA_LEVEL_SYNC)
     assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(B, nan=-1))
+    assert np.array_equal(np.nan_to_num(C32, nan=-1), np.nan_to_num(A[:32], nan=-1))
+    assert np.array_equal(np.nan_to_num(D32, nan=-1), np.nan_to_num(A[:32], nan=-1))
+    assert np.array_equal(np.nan_to_num(C20, nan=-1), np.nan_to_num(D20, nan=-1))
     for m in (0, 32):
         Ar = oracle.aread8(d, W[m], contcheck=False)
         assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(Ar, nan=-1))
