@@ -286,7 +286,7 @@ def Routing_GR2MSemiDistr(Model, Subbasins, Dem, AcumIni=None, AcumEnd=None, Sav
     """Weighted-Flow-Accumulation routing of Model$QS.  Returns dict(QR, Dates, COMID).
 
     `FlowDir` (int16 TauDEM codes) replaces the pitremove + D8Flowdir calls (Routing:88-93) when given;
-    otherwise d8prep.fill_and_flowdir derives one from `Dem` on the host (documented deviation)."""
+    otherwise wfa_flowdir_from_dem derives one from `Dem` on the device (own flat rule, documented)."""
     be = _capi
     t0 = time.perf_counter()
     QS = np.asarray(Model["QS"], np.float64)
@@ -299,8 +299,11 @@ def Routing_GR2MSemiDistr(Model, Subbasins, Dem, AcumIni=None, AcumEnd=None, Sav
         QS, dates = QS[i0:i1 + 1], dates[i0:i1 + 1]
     ntime, nsub = QS.shape
     if FlowDir is None:
-        from .d8prep import fill_and_flowdir
-        _, FlowDir = fill_and_flowdir(Dem.data[0], Dem.nodata)
+        z = np.asarray(Dem.data[0], np.float64)
+        valid = np.isfinite(z) & (z > -1e30)
+        if Dem.nodata is not None:
+            valid &= ~np.isclose(z, Dem.nodata, rtol=1e-6)
+        FlowDir = be.flowdir_from_dem(z, valid)
     src, off, cells = routing_geometry(Subbasins, Dem)
     if np.any(src < 0):
         raise ValueError("a subbasin's point on surface falls outside the DEM")

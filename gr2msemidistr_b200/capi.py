@@ -28,7 +28,7 @@ SYMBOLS = (
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_plan_basin_info", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
-    "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms",
+    "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem",
 )
 
 
@@ -273,6 +273,20 @@ class Plan:
 
     def mask_dev(self, ptr: int, nmonth: int, ld: int, flags: int = 0):
         _check(lib().wfa_mask_dev(self._h, C.c_int(nmonth), C.c_int(ld), C.c_void_p(ptr), C.c_int(flags)))
+
+
+def flowdir_from_dem(dem, valid, want_filled: bool = False):
+    """Depression fill + D8 directions on the device.  dem [nrow, ncol], valid bool mask.
+    Returns flowdir int16 (TauDEM codes, -32768 nodata) and optionally the filled surface."""
+    z = _f64(dem)
+    v = np.ascontiguousarray(valid, dtype=np.uint8)
+    if z.ndim != 2 or v.shape != z.shape:
+        raise ValueError("dem and valid must be 2-D arrays of the same shape")
+    fd = np.empty(z.shape, np.int16)
+    filled = np.empty(z.shape) if want_filled else None
+    _check(lib().wfa_flowdir_from_dem(_dp(z), v.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int(z.shape[0]),
+                                      C.c_int(z.shape[1]), fd.ctypes.data_as(C.POINTER(C.c_int16)), _dp(filled)))
+    return (fd, filled) if want_filled else fd
 
 
 def debug_math(op: int, x, y=None):

@@ -165,6 +165,14 @@ int wfa_plan_last_kernel_ms(wfa_plan *p, float *ms);
 /* split of the last sweep: wide levels (one launch each) and the thin tail */
 int wfa_plan_last_phase_ms(wfa_plan *p, float *wide_ms, float *tail_ms);
 
+/* ---- routing preprocessing: depression fill + D8 flow directions on the device ----------------
+ * Stands in for "pitremove" + "D8Flowdir" of Routing:88-93 (once per call).  dem, valid: [nrow x ncol]
+ * row-major, valid != 0 marks cells with data; flowdir (out): TauDEM codes 1..8, -32768 = nodata;
+ * filled (out, may be NULL): pit-filled elevations, NaN at invalid cells.  The flat-resolution rule is
+ * this library's own (see csrc/d8prep.cu); any D8 grid, e.g. TauDEM's, can be given to wfa_plan_create. */
+int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int nrow, int ncol, int16_t *flowdir,
+                         double *filled);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,13 @@ class Basin:
         return dict(of=r["of"][:, which].copy(), crit=r["crit"], qt=r["qt"])
 
 
+def flowdir_from_dem(dem, valid, want_filled=False):
+    from oracle import d8prep
+    z = np.where(valid, np.asarray(dem, float), np.nan)
+    filled, fd = d8prep.fill_and_flowdir(z)
+    return (fd, filled) if want_filled else fd
+
+
 class Plan:
     def __init__(self, flowdir, flags=0):
         self.d = np.asarray(flowdir, np.int16)

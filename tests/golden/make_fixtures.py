@@ -23,7 +23,8 @@ sys.path.insert(0, ROOT)
 RAW = "/root/reference/raw"
 
 import oracle  # noqa: E402
-from gr2msemidistr_b200 import api, d8prep, gis, synth  # noqa: E402
+from gr2msemidistr_b200 import api, gis, synth  # noqa: E402
+from oracle import d8prep  # noqa: E402
 
 
 def main():

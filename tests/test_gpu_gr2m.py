@@ -153,6 +153,24 @@ def test_objective_multi_tile_multi_region(capi, oracle, rng):
     _check_objective(capi, oracle, P, E, area, nd, region, nreg, synth.param_sets(9, nreg, seed=24), 0, flags=capi.PERC_F32_EXPONENT)
 
 
+def test_objective_extreme_parameter_sets(capi, oracle):
+    # corners of the calibration box, parameters below the airGR floor, the P/X1 > 13 clamp, factors that
+    # create exact decimal ties (1.186 * 25.0), zero and huge forcing -- through the calibration kernel
+    P, E, area, nd = synth.forcing(70, 96, seed=61)
+    P[0] = 0.0; E[1] = 0.0; P[2] = 3000.0; P[3, ::2] = 25.0; P[4] = 75.0
+    region = np.zeros(70, np.int32)
+    par = np.array([[1.0, 0.01, 0.8, 0.8], [2000.0, 2.0, 1.2, 1.2], [1.0, 2.0, 1.2, 0.8], [2000.0, 0.01, 0.8, 1.2],
+                    [0.001, 0.0, 1.0, 1.0], [10.976, 0.665, 1.186, 1.169], [500.0, 1.0, 1.0, 1.0], [50.0, 0.5, 1.15, 0.85]])
+    qobs = synth.qobs_from(np.full(96, 200.0))
+    for fl in (0, capi.MATH_LITERAL):
+        with capi.Basin(P, E, area, nd, region, 1) as b:
+            got = b.objective_batch(par, qobs, 12, capi.OF_NSE, fl | capi.SINK_UNROUNDED, want_qt=True)
+        ref = oracle.objective_batch(P, E, area, nd, region, 1, par, qobs, 12, flags=oracle.SINK_UNROUNDED, nthreads=4)
+        assert relerr(got["qt"], ref["qt"]) <= TOL
+        ok = np.isfinite(ref["crit"])
+        assert np.array_equal(np.isfinite(got["crit"]), ok) and relerr(got["crit"][ok], ref["crit"][ok]) <= TOL
+
+
 def test_objective_single_subbasin_branch(capi, oracle):
     # nsub == 1: sink is the unrounded QS (Optim:187-188)
     P, E, area, nd = synth.forcing(1, 120, seed=31)
