@@ -335,6 +335,8 @@ def main():
     ach_tf = units_kernel * FP64_INSTR_PER_UNIT * 2.0 / (kernel_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "traffic": None,
+                "traffic_note": "ncu --set full on a 1.2e10-unit slice of this workload (profiles/r1_calib2_step3_ncu_full.txt): "
+                                "0.27 GB of DRAM traffic per launch = 0.023 B per unit; the 4.8e11-unit launch is too long to replay",
                 "kernel": "k_gr2m_calib2<fast>" if not a.literal else "k_gr2m_calib2<literal>",
                 "peak_three_register_operand_dfma": peak_rrr,
                 "frac_of_three_register_operand_peak": ach_tf / peak_rrr,

@@ -4,6 +4,10 @@
 # the arithmetic is done by .Call into the C ABI, the wrappers keep only what must stay in R:
 # date handling, the parameter table, R's own round(), list assembly, file output.
 
+# flags for the C ABI: options(gr2m.perc_f32_exponent = TRUE) selects the percolation exponent gfortran
+# gives airGR's literal (1./3.) -- see DESIGN.md section 2; default is the exact cube root.
+.gr2m_flags <- function() if (isTRUE(getOption("gr2m.perc_f32_exponent"))) 1L else 0L
+
 .gr2m_dates <- function(x) as.POSIXct(paste0(x, " 00:00:00"), "GMT",
                                       tryFormats = c("%Y-%m-%d", "%Y/%m/%d", "%d-%m-%Y", "%d/%m/%Y"))
 
@@ -35,7 +39,7 @@ Run_GR2MSemiDistr <- function(Data, Subbasins, RunIni, RunEnd, WarmUp = NULL, Pa
   }
   message(paste("Running GR2M model for", s$nsub, "subbasins"))
   o <- .Call(C_gr2m_run, s$P, s$E, s$area, s$ndays, s$region_id, length(s$zone),
-             as.numeric(Parameters), S0, R0, 0L)
+             as.numeric(Parameters), S0, R0, .gr2m_flags())
   EndState <- lapply(seq_len(s$nsub), function(i)
     list(Store = list(Prod = o$S_end[i], Rout = o$R_end[i], Exp = NA), UH = list(UH1 = NA, UH2 = NA)))
   pr <- round(o$PR, 1); ae <- round(o$AE, 1); sm <- round(o$SM, 1); ru <- round(o$RU, 1)
@@ -64,7 +68,7 @@ gr2m_objective_batch <- function(handle, parameter_sets, Qobs, WarmUp = 0L,
                                  Optimization = c("KGE", "NSE", "RMSE")) {
   which <- match(match.arg(Optimization), c("KGE", "NSE", "RMSE")) - 1L
   .Call(C_gr2m_objective, handle, as.matrix(parameter_sets) * 1.0, as.numeric(Qobs),
-        as.integer(WarmUp), which, 0L)
+        as.integer(WarmUp), which, .gr2m_flags())
 }
 
 Optim_GR2MSemiDistr <- function(Data, Subbasins, RunIni, RunEnd, WarmUp = NULL, Parameters,
