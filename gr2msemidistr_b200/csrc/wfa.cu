@@ -688,13 +688,15 @@ __global__ void k_cells_to_planes(const T *__restrict__ in, long long ncell, int
 }
 
 // Weight[index$cells] <- QS[i,]  (Routing:109-113); src < 0 marks an overwritten duplicate
+// months [t0, t0 + nt) of the ntime-month series go to columns 0..nt-1 of the sweep buffer
 template <typename T>
-__global__ void k_scatter(const double *__restrict__ QS, const int32_t *__restrict__ src, int nsub, int ntime, T *A, int ld)
+__global__ void k_scatter(const double *__restrict__ QS, const int32_t *__restrict__ src, int nsub, int ntime, int t0,
+                          int nt, T *A, int ld)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int s = idx / ntime, t = idx % ntime;
+    int s = idx / nt, t = idx % nt;
     if (s >= nsub || src[s] < 0) return;
-    A[(size_t)src[s] * ld + t] = (T)QS[(size_t)s * ntime + t];
+    A[(size_t)src[s] * ld + t] = (T)QS[(size_t)s * ntime + t0 + t];
 }
 
 // max(values[coverage_fraction == 1], na.rm = TRUE) per polygon and month (Routing:119-121).
@@ -703,12 +705,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_polygon_max(const int32_t *__restrict__ poff, const int32_t *__restrict__ pcells,
                                                      const int32_t *__restrict__ level, const uint8_t *__restrict__ contam,
                                                      int use_contam, const T *__restrict__ A, int ld, int ntime,
-                                                     double *__restrict__ QR)
+                                                     int t0, int nt, double *__restrict__ QR)
 {
     __shared__ double sm[8][32];
     const int s = blockIdx.x, t = blockIdx.y * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
     double m = -INFINITY;
-    if (t < ntime)
+    if (t < nt)
         for (int q = poff[s] + w; q < poff[s + 1]; q += 8) {
             int32_t c = pcells[q];
             if (level[c] < 0 || (use_contam && contam[c])) continue;
@@ -717,10 +719,10 @@ __global__ void __launch_bounds__(256) k_polygon_max(const int32_t *__restrict__
         }
     sm[w][threadIdx.x & 31] = m;
     __syncthreads();
-    if (w == 0 && t < ntime) {
+    if (w == 0 && t < nt) {
 #pragma unroll
         for (int k = 1; k < 8; ++k) m = fmax(m, sm[k][threadIdx.x]);
-        QR[(size_t)s * ntime + t] = m;
+        QR[(size_t)s * ntime + t0 + t] = m;
     }
 }
 
@@ -1265,8 +1267,15 @@ extern "C" int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, con
         for (int i = 0; i + 1 < nsub; ++i)
             if (src_cell[idx[i]] == src_cell[idx[i + 1]]) src[idx[i]] = -1;
     }
-    const int ld = ceil_div(ntime, 4) * 4;
+    // months are swept in chunks so the dense buffer stays within ~16 GB whatever the grid size;
+    // chunks of <= 32 months also take the shared-memory-forwarding per-basin kernel
     const size_t esz = (flags & WFA_F32) ? 4 : 8;
+    long long budget = 16ll << 30;
+    if (const char *ev = getenv("WFA_ROUTE_BUDGET_MB")) budget = std::max(1ll, atoll(ev)) << 20;   // test knob
+    long long fit = budget / ((long long)n * (long long)esz);
+    int chunk = fit >= ntime ? ntime : (int)std::max<long long>(32, fit / 32 * 32);
+    if (chunk > ntime) chunk = ntime;
+    const int ld = ceil_div(chunk, 4) * 4;
     int rc;
     if ((rc = p->work2.ensure((size_t)n * ld * esz))) return rc;
     if ((rc = p->qs.ensure((size_t)nsub * ntime * 8))) return rc;
@@ -1275,30 +1284,35 @@ extern "C" int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, con
     if ((rc = p->poff.ensure(((size_t)nsub + 1) * 4))) return rc;
     if ((rc = p->pcells.ensure(std::max<size_t>(4, (size_t)npc * 4)))) return rc;
     cudaStream_t st = p->stream;
-    CK(cudaMemsetAsync(p->work2.p, 0, (size_t)n * ld * esz, st));
     CK(cudaMemcpyAsync(p->qs.p, QS, (size_t)nsub * ntime * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(p->src.p, src.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(p->poff.p, poly_off, ((size_t)nsub + 1) * 4, cudaMemcpyHostToDevice, st));
     if (npc) CK(cudaMemcpyAsync(p->pcells.p, poly_cells, (size_t)npc * 4, cudaMemcpyHostToDevice, st));
-    const int nb = ceil_div((long long)nsub * ntime, 256);
     const int use_contam = (flags & WFA_NO_CONTAMINATION) ? 0 : 1;
-    dim3 pg(nsub, ceil_div(ntime, 32));
-    if (flags & WFA_F32) {
-        k_scatter<float><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, p->work2.as<float>(), ld);
+    for (int t0 = 0; t0 < ntime; t0 += chunk) {
+        const int nt = std::min(chunk, ntime - t0);
+        const int nb = ceil_div((long long)nsub * nt, 256);
+        dim3 pg(nsub, ceil_div(nt, 32));
+        CK(cudaMemsetAsync(p->work2.p, 0, (size_t)n * ld * esz, st));
+        if (flags & WFA_F32) {
+            k_scatter<float><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
+                                                 p->work2.as<float>(), ld);
+            CK(cudaGetLastError());
+            if ((rc = wfa_accumulate_dev(p, nt, ld, p->work2.p, flags))) return rc;
+            k_polygon_max<float><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+                                                     p->contam.as<uint8_t>(), use_contam, p->work2.as<float>(), ld, ntime,
+                                                     t0, nt, p->qr.as<double>());
+        } else {
+            k_scatter<double><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
+                                                  p->work2.as<double>(), ld);
+            CK(cudaGetLastError());
+            if ((rc = wfa_accumulate_dev(p, nt, ld, p->work2.p, flags))) return rc;
+            k_polygon_max<double><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+                                                      p->contam.as<uint8_t>(), use_contam, p->work2.as<double>(), ld,
+                                                      ntime, t0, nt, p->qr.as<double>());
+        }
         CK(cudaGetLastError());
-        if ((rc = wfa_accumulate_dev(p, ntime, ld, p->work2.p, flags))) return rc;
-        k_polygon_max<float><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
-                                                 p->contam.as<uint8_t>(), use_contam, p->work2.as<float>(), ld, ntime,
-                                                 p->qr.as<double>());
-    } else {
-        k_scatter<double><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, p->work2.as<double>(), ld);
-        CK(cudaGetLastError());
-        if ((rc = wfa_accumulate_dev(p, ntime, ld, p->work2.p, flags))) return rc;
-        k_polygon_max<double><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
-                                                  p->contam.as<uint8_t>(), use_contam, p->work2.as<double>(), ld, ntime,
-                                                  p->qr.as<double>());
     }
-    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(QR, p->qr.p, (size_t)nsub * ntime * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return GR2M_OK;

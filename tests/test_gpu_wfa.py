@@ -118,6 +118,22 @@ def test_route_matches_oracle_c1_shape(capi, oracle, rng):
     assert np.array_equal(QRnc, oracle.route(d, QS, src, off, cells, contcheck=False, nthreads=8))
 
 
+def test_route_month_chunking_is_invisible(capi, rng, monkeypatch):
+    # big grids are routed in month chunks to bound the dense buffer; the result must not change
+    nrow, ncol = 251, 429
+    d = synth.d8_grid(nrow, ncol, seed=13).numpy()
+    src, off, cells = synth.block_polygons(nrow, ncol, 3, 5, margin=3)
+    QS = rng.uniform(0, 400, (15, 100))
+    with capi.Plan(d) as p:
+        whole = p.route(QS, src, off, cells)
+        monkeypatch.setenv("WFA_ROUTE_BUDGET_MB", "30")          # 107 679 cells x 8 B -> chunks of 32 months
+        chunked = p.route(QS, src, off, cells)
+        chunked32 = p.route(QS, src, off, cells, capi.WFA_F32)
+        monkeypatch.delenv("WFA_ROUTE_BUDGET_MB")
+        whole32 = p.route(QS, src, off, cells, capi.WFA_F32)
+    assert np.array_equal(whole, chunked) and np.array_equal(whole32, chunked32)
+
+
 def test_route_edge_cases(capi, oracle, rng):
     nrow, ncol = 96, 128
     d = synth.d8_grid(nrow, ncol).numpy()
