@@ -84,3 +84,20 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "gr2m_oracle" not in txt and "orc_" not in txt, f
+
+
+def test_header_is_plain_c_and_a_c_caller_links(capi, tmp_path):
+    """include/gr2m_b200.h must be consumable from C (R's .Call shim, cgo, ...): build examples/c_abi_demo.c
+    as strict C99 against the shared library and run it; without a GPU it reports that and exits 0."""
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lgr2m_b200",
+                           f"-Wl,-rpath,{libdir}", "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ABI version 1" in out.stdout
+    if capi.device_count() == 0:
+        assert "no GPU here" in out.stdout
+    else:
+        assert "set 0: 1 - NSE = 0.000" in out.stdout

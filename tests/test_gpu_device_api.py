@@ -94,3 +94,17 @@ def test_errors_are_reported_not_fatal(capi):
     assert lib.gr2m_set_device(99) == capi.ERR_INVALID
     with pytest.raises(ValueError):
         capi.Plan(np.ones((3, 3), np.int16)).accumulate(np.ones((2, 2)))     # wrong grid shape
+
+
+def test_plain_c_caller_runs_on_the_gpu(capi, tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "examples", "c_abi_demo.c"), "-L", libdir, "-lgr2m_b200",
+                           f"-Wl,-rpath,{libdir}", "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "set 0: 1 - NSE = 0.000" in out.stdout and "set 1:" in out.stdout
