@@ -221,8 +221,10 @@ def bench_routing(a, capi, torch, rank, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     units = float(ncell) * months_total
-    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    if os.path.exists(peaks_file):
+        hbm, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     gbs = units / world * 16.0 / (ms * 1e-3) / 1e9
     out = {"metric": "routed_cell_months_per_sec", "value": units / (ms * 1e-3), "unit": UNIT,
            "workload": f"C5 WFA: {n} x {n} synthetic D8 grid x {months_total} months, dense FP64 weights, "
@@ -230,7 +232,10 @@ def bench_routing(a, capi, torch, rank, world, dist):
            "ms_per_pass": ms, "levels": plan.nlevels, "cells_in_order": plan.norder,
            "plan_build_s": t_plan, "grid_gen_s": t_gen,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                        "traffic": None, "algorithmic_bytes_per_unit": 16}}
+                        "traffic": None, "algorithmic_bytes_per_unit": 16, "peak_source": hbm_src,
+                        "traffic_note": "ncu --set full, widest level of an 8000^2 grid x 32 months: 6.2 GB DRAM traffic in "
+                                        "1.11 ms (5.6 TB/s) = own row + upstream rows + write, about 17 B per cell-month "
+                                        "(profiles/r1_route_ncu_full.txt)"}}
     out["basins"] = plan.basin_info()
     plan.close()
     del A
