@@ -403,6 +403,27 @@ def main():
     else:
         basin.close()
 
+    # ---- simulation mode (Run_GR2MSemiDistr: one parameter set, every series written) -------------
+    simulation = None
+    if rank == 0:
+        try:
+            with capi.Basin(P, E, area, nd, region, 1) as bs:
+                bs.run(par_all[0], outputs=("QS",))
+                t0 = time.perf_counter()
+                bs.run(par_all[0])
+                dt = time.perf_counter() - t0
+                kms = bs.last_kernel_ms()
+            u = float(a.cells) * a.months
+            simulation = {"metric": "gr2m_cell_months_per_sec (simulation mode, 1 set, PR/AE/SM/RU/QS written)",
+                          "workload": f"{a.cells} subbasins x {a.months} months x 1 parameter set",
+                          "kernel_ms": kms, "kernel_value": u / (kms * 1e-3),
+                          "e2e_value": u / dt, "e2e_note": "gr2m_run incl. 5 transposes and 5 x D2H of [ntime x ncell] doubles",
+                          "roofline": {"bound": "hbm", "achieved": u * 56.0 / (kms * 1e-3) / 1e9, "unit": "GB/s",
+                                       "algorithmic_bytes_per_unit": 56,
+                                       "note": "launch-latency sized (one thread per subbasin): reported, not tuned"}}
+        except Exception as ex:
+            simulation = {"error": repr(ex)}
+
     routing = None
     if a.route_n > 0:
         try:
@@ -422,7 +443,7 @@ def main():
                            "l2": "forcing (768 MB) and outlet partials larger than L2; no flush needed",
                            "parallelism": f"parameter sets sharded over {world} GPU(s), forcing replicated"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": 2 * a.steps, "clocks": clocks, "routing": routing,
+                "gpu_launches": 2 * a.steps, "clocks": clocks, "routing": routing, "simulation": simulation,
                 "objective_checksum": float(np.nansum(of_host))}
         print(json.dumps(line), flush=True)
     if world > 1:
