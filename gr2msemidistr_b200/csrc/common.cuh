@@ -33,6 +33,28 @@ int gr2m_current_device(void);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// grow-only device buffer owned by a handle (capacity kept across calls)
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return GR2M_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return GR2M_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+
 // ---- warp helpers -----------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ double shfl_xor_f64(double v, int m)

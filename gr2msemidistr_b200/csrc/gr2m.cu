@@ -411,25 +411,6 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return GR2M_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        CK(cudaMalloc(&p, bytes));
-        cap = bytes;
-        return GR2M_OK;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-    }
-    template <typename T> T *as() { return static_cast<T *>(p); }
-};
 
 struct gr2m_basin {
     int device = 0, ntime = 0, ntime_pad = 0, ncell = 0, ncell_pad = 0, ntiles = 0, nreg = 0;

@@ -726,25 +726,6 @@ __global__ void __launch_bounds__(256) k_polygon_max(const int32_t *__restrict__
     }
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return GR2M_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        CK(cudaMalloc(&p, bytes));
-        cap = bytes;
-        return GR2M_OK;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-    }
-    template <typename T> T *as() { return static_cast<T *>(p); }
-};
 
 constexpr int COMP_WIDTH = 16384;     // per-basin sweep starts where every later level is at most this wide
 constexpr int THIN_LIMIT = 2048;      // plan peeling: frontiers this small are peeled inside one CTA
