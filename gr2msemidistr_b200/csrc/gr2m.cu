@@ -2,8 +2,8 @@
 //
 // Data layout in HBM (owned by gr2m_basin):
 //   F      tiled month-major forcing  F[tile][t][var][lane]  doubles, tile = 32 consecutive cells,
-//          var 0 = P, 1 = E, t < ntime_pad (ntime rounded up to TM months, zero padded).  One stage of
-//          TM months of one tile is ONE contiguous TM*512-byte block, fetched by a single 1-D bulk
+//          var 0 = P, 1 = E, t < ntime_pad (ntime rounded up to 16 months, zero padded).  One stage of
+//          8 months of one tile is ONE contiguous 4 KiB block, fetched by a single 1-D bulk
 //          async copy (TMA engine, UBLKCP) into shared memory and shared by all sets of the block;
 //          inside a stage the 32 lanes of a warp read 32 consecutive doubles (coalesced, conflict-free).
 //   area, region   per cell;  den[t] = 86.4*nDays[t], conv[t] = 1/den[t]   (Run:229)

@@ -8,9 +8,12 @@
 // Sweep: accumulation buffer A[cell][ld] is cell-major with the month batch contiguous, so one
 // sub-warp group handles one cell with the months on its lanes: every upstream row is one coalesced
 // read, and a cell's sum is taken in TauDEM's fixed k = 1..8 neighbour order -- deterministic with
-// no atomics and no cross-lane reduction.  Cells of one level are independent; levels are
-// swept in order: wide levels as one launch each, the long thin tail by a single resident CTA
-// (level-synchronous mode) or by a flag-driven dataflow kernel (default).
+// no atomics and no cross-lane reduction.  Cells of one level are independent; levels are swept in
+// order: the wide levels below a cut as one launch each (bandwidth-bound), the levels above it per
+// outlet basin -- the upper network is a forest of independent trees, one CTA walks one tree with
+// block barriers only (k_accum_components*).  When the forest does not split into enough trees the
+// upper levels are swept grid-wide instead: one launch per level, then a single resident CTA for the
+// long thin tail (WFA_LEVEL_SYNC), or a ticketed flag-driven dataflow kernel (WFA_DATAFLOW).
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
