@@ -113,8 +113,11 @@ Routing_GR2MSemiDistr <- function(Model, Subbasins, Dem, AcumIni = NULL, AcumEnd
   cov  <- exactextractr::exact_extract(Dem, roi, include_cell = TRUE, progress = FALSE)
   inner <- lapply(cov, function(d) d$cell[d$coverage_fraction == 1] - 1L)
   off  <- as.integer(c(0, cumsum(lengths(inner))))
-  if (is.null(FlowDir)) stop("pass FlowDir (TauDEM D8 codes as a RasterLayer): pitremove/D8Flowdir stay outside the library")
-  fd <- raster::as.matrix(FlowDir); storage.mode(fd) <- "integer"
+  if (is.null(FlowDir)) {           # no TauDEM: pit filling + D8 codes on the GPU (own flat rule, see DESIGN.md)
+    fd <- .Call(C_wfa_flowdir, raster::as.matrix(Dem) * 1.0)
+  } else {                          # FlowDir.tif of "D8Flowdir -p" as a RasterLayer
+    fd <- raster::as.matrix(FlowDir); storage.mode(fd) <- "integer"
+  }
   message(paste0("Routing streamflows for ", ncol(QS), " sub-basins"))
   qr <- round(.Call(C_wfa_route, fd, QS * 1.0, as.integer(src), off, as.integer(unlist(inner)), 0L), 1)
   Ans <- list(QR = qr, Dates = Dates, COMID = as.vector(roi$COMID))
@@ -128,8 +131,9 @@ Routing_GR2MSemiDistr <- function(Model, Subbasins, Dem, AcumIni = NULL, AcumEnd
   for (k in keys) {
     new <- as.data.frame(Ans[[k]]); colnames(new) <- paste0(k, "_", Ans$COMID); rownames(new) <- Ans$Dates
     if (Update) {
-      m1 <- format(lubridate::floor_date(Sys.Date() - months(2), "month"), "%Y%m")
-      m2 <- format(lubridate::floor_date(Sys.Date() - months(1), "month"), "%Y%m")
+      first <- as.Date(format(Sys.Date(), "%Y-%m-01"))      # month arithmetic without attaching lubridate
+      m1 <- format(seq(first, by = "-2 month", length.out = 2)[2], "%Y%m")
+      m2 <- format(seq(first, by = "-1 month", length.out = 2)[2], "%Y%m")
       f1 <- file.path("Outputs", paste0(k, "_GR2MSemiDistr_", m1, ".txt"))
       old <- utils::read.table(f1, header = TRUE, sep = "\t")
       all <- rbind(as.matrix(old), as.matrix(new)); rownames(all) <- c(rownames(old), rownames(new))

@@ -85,11 +85,39 @@ SEXP C_wfa_route(SEXP flowdir, SEXP QS, SEXP src_cell, SEXP poly_off, SEXP poly_
     return QR;
 }
 
+/* dem: numeric matrix (nrow x ncol, column-major, NA = nodata) -> integer matrix of TauDEM D8 codes (NA = nodata) */
+SEXP C_wfa_flowdir(SEXP dem)
+{
+    int nrow = Rf_nrows(dem), ncol = Rf_ncols(dem);
+    size_t n = (size_t)nrow * ncol;
+    double *z = (double *)R_alloc(n, sizeof(double));
+    uint8_t *valid = (uint8_t *)R_alloc(n, 1);
+    int16_t *fd = (int16_t *)R_alloc(n, sizeof(int16_t));
+    const double *d = REAL(dem);
+    for (int r = 0; r < nrow; ++r)
+        for (int c = 0; c < ncol; ++c) {
+            double v = d[(size_t)c * nrow + r];
+            valid[(size_t)r * ncol + c] = (uint8_t)(R_FINITE(v) ? 1 : 0);
+            z[(size_t)r * ncol + c] = R_FINITE(v) ? v : 0.0;
+        }
+    fail(wfa_flowdir_from_dem(z, valid, nrow, ncol, fd, NULL));
+    SEXP out = PROTECT(Rf_allocMatrix(INTSXP, nrow, ncol));
+    int *o = INTEGER(out);
+    for (int r = 0; r < nrow; ++r)
+        for (int c = 0; c < ncol; ++c) {
+            int16_t v = fd[(size_t)r * ncol + c];
+            o[(size_t)c * nrow + r] = v > 0 ? (int)v : NA_INTEGER;
+        }
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"C_gr2m_run", (DL_FUNC)&C_gr2m_run, 10},
     {"C_gr2m_basin", (DL_FUNC)&C_gr2m_basin, 6},
     {"C_gr2m_objective", (DL_FUNC)&C_gr2m_objective, 6},
     {"C_wfa_route", (DL_FUNC)&C_wfa_route, 6},
+    {"C_wfa_flowdir", (DL_FUNC)&C_wfa_flowdir, 1},
     {NULL, NULL, 0}};
 
 void R_init_GR2MSemiDistrB200(DllInfo *dll)
