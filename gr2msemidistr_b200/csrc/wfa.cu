@@ -597,6 +597,336 @@ __global__ void __launch_bounds__(288) k_accum_components_fw(const int32_t *__re
     }
 }
 
+
+// ---- upper network by river reach -----------------------------------------------------------------
+// Above the cut most cells have exactly one upstream cell that is itself above the cut: they form
+// reaches (maximal chains between confluences of upper branches).  Along a reach the only value on
+// the dependency chain is the predecessor's, which the sweeping warp keeps in a register; everything
+// else a cell adds is final before the reach starts.  Reaches are ordered by reach level (0 = fed from
+// below the cut only, else 1 + max over the reaches that join at its head); one launch sweeps all
+// reaches of a level, one lane group per reach.  The latency chain of the upper phase thus shrinks from
+// "longest river in LEVELS x a barrier and an L2 round trip" to "sum over reach levels of the longest
+// reach in CELLS x a few dependent adds".
+constexpr uint32_t UP_PRED = 0x80000000u;     // rup_idx entry: the in-reach predecessor
+
+__global__ void k_run_upos(const int32_t *__restrict__ uorder, int nu, int32_t *__restrict__ upos)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nu) upos[uorder[j]] = j;
+}
+
+// pred[j] = position of the only upper upstream cell, or -1 (reach head); npu[j] = number of upper upstream cells
+__global__ void k_run_pred(const int32_t *__restrict__ uorder, int nu, int ncol, int cut,
+                           const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level,
+                           const int32_t *__restrict__ upos, int32_t *__restrict__ pred, uint8_t *__restrict__ npu)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu) return;
+    int32_t c = uorder[j];
+    unsigned m = inmask[c];
+    int cnt = 0, last = -1;
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        int32_t u = c + c_dy[k] * ncol + c_dx[k];
+        if (level[u] >= cut) { ++cnt; last = upos[u]; }
+    }
+    npu[j] = (uint8_t)cnt;
+    pred[j] = cnt == 1 ? last : -1;
+}
+
+__global__ void k_run_rank_init(const int32_t *__restrict__ pred, int nu, int32_t *__restrict__ head,
+                                int32_t *__restrict__ dist)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu) return;
+    head[j] = pred[j] < 0 ? j : pred[j];
+    dist[j] = pred[j] < 0 ? 0 : 1;
+}
+
+// pointer jumping (ping-pong buffers): head -> head of head, dist accumulates
+__global__ void k_run_rank_step(const int32_t *__restrict__ hs, const int32_t *__restrict__ ds, int nu,
+                                int32_t *__restrict__ hd, int32_t *__restrict__ dd, int *__restrict__ changed)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu) return;
+    int32_t h = hs[j], hh = hs[h];
+    hd[j] = hh;
+    dd[j] = ds[j] + (hh != h ? ds[h] : 0);
+    if (hh != h) *changed = 1;
+}
+
+// reach level of the heads by monotone relaxation (values only grow; fixed point = the definition)
+__global__ void k_run_level_step(const int32_t *__restrict__ uorder, int nu, int ncol, int cut,
+                                 const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level,
+                                 const int32_t *__restrict__ upos, const int32_t *__restrict__ head,
+                                 const uint8_t *__restrict__ npu, int32_t *rl, int *__restrict__ changed)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu || npu[j] < 2) return;             // heads fed by upper reaches only
+    int32_t c = uorder[j];
+    unsigned m = inmask[c];
+    int best = 0;
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        int32_t u = c + c_dy[k] * ncol + c_dx[k];
+        if (level[u] >= cut) best = max(best, 1 + ((volatile int32_t *)rl)[head[upos[u]]]);
+    }
+    if (best > rl[j]) { rl[j] = best; *changed = 1; }
+}
+
+__global__ void k_run_keys(const int32_t *__restrict__ head, const int32_t *__restrict__ dist,
+                           const int32_t *__restrict__ rl, int nu, unsigned long long *__restrict__ keys,
+                           int32_t *__restrict__ vals)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu) return;
+    int32_t h = head[j];
+    keys[j] = ((unsigned long long)rl[h] << 48) | ((unsigned long long)h << 20) | (unsigned long long)dist[j];
+    vals[j] = j;
+}
+
+// after the sort: cells in sweep order, reach starts flagged, upstream counts
+__global__ void k_run_gather(const int32_t *__restrict__ sj, int nu, const int32_t *__restrict__ uorder,
+                             const int32_t *__restrict__ dist, const uint8_t *__restrict__ inmask,
+                             int32_t *__restrict__ rcell, int32_t *__restrict__ isstart, int32_t *__restrict__ cnt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int j = sj[i];
+    int32_t c = uorder[j];
+    rcell[i] = c;
+    isstart[i] = dist[j] == 0;
+    cnt[i] = __popc(inmask[c]);
+}
+
+__global__ void k_run_starts(const int32_t *__restrict__ isstart, const int32_t *__restrict__ rank, int nu,
+                             int32_t *__restrict__ run_start)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nu && isstart[i]) run_start[rank[i] - 1] = i;      // rank = inclusive scan of isstart
+}
+
+__global__ void k_run_upfill(const int32_t *__restrict__ sj, int nu, int ncol, const int32_t *__restrict__ rcell,
+                             const uint8_t *__restrict__ inmask, const int32_t *__restrict__ pred,
+                             const int32_t *__restrict__ uorder, const int32_t *__restrict__ rup_off,
+                             uint32_t *__restrict__ rup_idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int32_t c = rcell[i];
+    int pj = pred[sj[i]];
+    int32_t pc = pj >= 0 ? uorder[pj] : -1;
+    unsigned m = inmask[c];
+    int q = rup_off[i];
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        int32_t u = c + c_dy[k] * ncol + c_dx[k];
+        rup_idx[q++] = (uint32_t)u | (u == pc ? UP_PRED : 0u);
+    }
+}
+
+// reach level of every reach (run) and the first reach of every level
+__global__ void k_run_levels(const int32_t *__restrict__ run_start, int nr, const int32_t *__restrict__ sj,
+                             const int32_t *__restrict__ rl, int32_t *__restrict__ run_rl)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nr) run_rl[r] = rl[sj[run_start[r]]];
+}
+
+// rows a cell contributes to the reach stream: none for a reach head, else 1 (own weight + the side
+// inflows that precede the predecessor in k order) + one per side inflow after the predecessor
+__global__ void k_run_rows(const int32_t *__restrict__ isstart, const int32_t *__restrict__ rup_off,
+                           const uint32_t *__restrict__ rup_idx, int nu, int32_t *__restrict__ rows)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int r = 0;
+    if (!isstart[i]) {
+        const int o = rup_off[i], n = rup_off[i + 1] - o;
+        int q = 0;
+        while (q < n && !(rup_idx[o + q] & UP_PRED)) ++q;
+        r = n - q;                                  // 1 + entries after the predecessor
+    }
+    rows[i] = r;
+}
+
+// rowcell[r] = the cell whose sum is complete after stream row r, or -1
+__global__ void k_run_rowcell(const int32_t *__restrict__ row_off, const int32_t *__restrict__ rcell, int nu,
+                              int32_t *__restrict__ rowcell)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    const int b = row_off[i], e = row_off[i + 1];
+    for (int r = b; r < e; ++r) rowcell[r] = r == e - 1 ? rcell[i] : -1;
+}
+
+// per reach: first/last stream row, head cell and the head's inflow list, in one 48-byte record
+__global__ void k_run_pack(const int32_t *__restrict__ run_start, int nr, const int32_t *__restrict__ rcell,
+                           const int32_t *__restrict__ rup_off, const uint32_t *__restrict__ rup_idx,
+                           const int32_t *__restrict__ row_off, int4 *__restrict__ rinfo)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nr) return;
+    const int i0 = run_start[r], i1 = run_start[r + 1];
+    const int o = rup_off[i0], n = rup_off[i0 + 1] - o;
+    uint32_t u[8];
+    for (int q = 0; q < 8; ++q) u[q] = q < n ? (rup_idx[o + q] & UP_ID) : 0u;
+    rinfo[3 * r + 0] = make_int4(row_off[i0], row_off[i1], rcell[i0], n);
+    rinfo[3 * r + 1] = make_int4((int)u[0], (int)u[1], (int)u[2], (int)u[3]);
+    rinfo[3 * r + 2] = make_int4((int)u[4], (int)u[5], (int)u[6], (int)u[7]);
+}
+
+// Phase 1 of the reach sweep, fully parallel: everything a non-head cell adds besides its predecessor is
+// final once the levels below the cut are done.  Write it as a dense stream in sweep order, so that the
+// serial phase reads consecutive memory (no index chasing, no TLB misses on its latency chain):
+//   row_off[i]      : own + side inflows before the predecessor (summed in k order, as AreaD8 does)
+//   row_off[i]+1... : the side inflows after the predecessor, one row each (their order matters)
+// A running sum over the rows of a reach then reproduces the k-ordered additions bit for bit, since
+// (own + a) + chain == chain + (own + a) in IEEE arithmetic.
+// A lane group takes G consecutive cells: the sweep metadata is read one cell per lane (coalesced) and
+// handed round by shuffles, so that only the row loads themselves see memory latency.
+template <typename T, int G>
+__global__ void __launch_bounds__(256) k_reach_gather(const int32_t *__restrict__ rcell,
+                                                      const int32_t *__restrict__ rup_off,
+                                                      const uint32_t *__restrict__ rup_idx,
+                                                      const int32_t *__restrict__ row_off, int nu,
+                                                      const T *__restrict__ A, T *__restrict__ S, int ld, int lds,
+                                                      int nmonth)
+{
+    const long long ib = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G * G;
+    const int g = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
+    if (ib >= nu) return;
+    int m_rb = 0, m_nr = 0, m_c = 0, m_o = 0, m_n = 0;
+    uint32_t m_e0 = UP_PRED, m_e1 = UP_PRED, m_e2 = UP_PRED;
+    if (ib + g < nu) {
+        const int i = (int)ib + g;
+        m_rb = row_off[i]; m_nr = row_off[i + 1] - m_rb;
+        m_c = rcell[i]; m_o = rup_off[i]; m_n = rup_off[i + 1] - m_o;
+    }
+    if (m_nr > 0) {
+        m_e0 = rup_idx[m_o];
+        if (m_n > 1) m_e1 = rup_idx[m_o + 1];
+        if (m_n > 2) m_e2 = rup_idx[m_o + 2];
+    }
+    const int cnt = (int)min((long long)G, nu - ib);
+#pragma unroll 4
+    for (int s = 0; s < cnt; ++s) {
+        const int nr = __shfl_sync(gmask, m_nr, s, G);
+        const int rb = __shfl_sync(gmask, m_rb, s, G);
+        const int c = __shfl_sync(gmask, m_c, s, G);
+        const int n = __shfl_sync(gmask, m_n, s, G);
+        const int o = __shfl_sync(gmask, m_o, s, G);
+        const uint32_t e0 = __shfl_sync(gmask, m_e0, s, G);
+        const uint32_t e1 = __shfl_sync(gmask, m_e1, s, G);
+        const uint32_t e2 = __shfl_sync(gmask, m_e2, s, G);
+        if (nr == 0) continue;                    // reach head: summed from A by the sweep itself
+        for (int j = g; j < nmonth; j += G) {
+            T acc = __ldcs(A + (size_t)c * ld + j);
+            const T v0 = (e0 & UP_PRED) ? (T)0 : __ldcs(A + (size_t)e0 * ld + j);
+            const T v1 = (e1 & UP_PRED) ? (T)0 : __ldcs(A + (size_t)e1 * ld + j);
+            const T v2 = (e2 & UP_PRED) ? (T)0 : __ldcs(A + (size_t)e2 * ld + j);
+            int r = rb;
+            bool after = false;
+            auto put = [&](uint32_t e, T v) {
+                if (e & UP_PRED) after = true;
+                else if (!after) acc += v;
+                else __stcs(S + (size_t)(++r) * lds + j, v);
+            };
+            put(e0, v0);
+            if (n > 1) put(e1, v1);
+            if (n > 2) put(e2, v2);
+            for (int q = 3; q < n; ++q) {
+                const uint32_t e = rup_idx[o + q];
+                put(e, (e & UP_PRED) ? (T)0 : __ldcs(A + (size_t)e * ld + j));
+            }
+            __stcs(S + (size_t)rb * lds + j, acc);
+        }
+    }
+}
+
+// Phase 2: one warp per reach, months on the lanes, the reaches of one reach level per launch.  The head
+// is summed from A (its inflows are tails of earlier reaches or lie below the cut); after it the sweep
+// is a running sum over the reach's rows of the stream, stored to A wherever a cell completes.  The
+// stream (and the matching rowcell entries) arrives through a per-warp ring of bulk async copies, RS_ROWS
+// rows per stage and RS_STAGES stages ahead, so the chain sees shared-memory latency only.
+constexpr int RS_ROWS = 16, RS_STAGES = 4, RS_WARPS = 2;
+
+template <typename T>
+__global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__restrict__ rinfo,
+                                                              const int32_t *__restrict__ rowcell, int r0, int r1,
+                                                              const T *__restrict__ S, int lds, T *A, int ld,
+                                                              int nmonth)
+{
+    __shared__ alignas(128) T sbuf[RS_WARPS][RS_STAGES][RS_ROWS][32];
+    __shared__ alignas(16) int32_t scell[RS_WARPS][RS_STAGES][RS_ROWS];
+    __shared__ alignas(8) uint64_t full[RS_WARPS][RS_STAGES];
+    const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int run = r0 + blockIdx.x * RS_WARPS + w;
+    if (run >= r1) return;                        // warps never meet at a block barrier
+    if (lane == 0) {
+        for (int i = 0; i < RS_STAGES; ++i) mbar_init(&full[w][i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int4 h0 = __ldg(rinfo + 3 * (size_t)run), h1 = __ldg(rinfo + 3 * (size_t)run + 1),
+               h2 = __ldg(rinfo + 3 * (size_t)run + 2);
+    const int rbeg = h0.x, rend = h0.y, c0 = h0.z, n0 = h0.w;
+    const int up[8] = {h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w};
+    const int b0 = rbeg / RS_ROWS, nblk = rend > rbeg ? (rend + RS_ROWS - 1) / RS_ROWS - b0 : 0;
+    int done = 0;                                 // stream blocks consumed so far over all passes (ring position)
+    for (int j0 = 0; j0 < nmonth; j0 += 32) {
+        const int j = j0 + lane;
+        const bool live = j < nmonth;
+        const uint32_t segbytes = (uint32_t)min(32, lds - j0) * (uint32_t)sizeof(T);
+        auto issue = [&](int k, int pos) {        // stream block b0+k into ring slot pos % RS_STAGES
+            const int st = pos % RS_STAGES;
+            const size_t row = (size_t)(b0 + k) * RS_ROWS;
+            if (lane == 0) mbar_arrive_expect_tx(&full[w][st], RS_ROWS * segbytes + RS_ROWS * 4);
+            __syncwarp();
+            if (lane < RS_ROWS) bulk_g2s(&sbuf[w][st][lane][0], S + (row + lane) * lds + j0, segbytes, &full[w][st]);
+            if (lane == RS_ROWS) bulk_g2s(&scell[w][st][0], rowcell + row, RS_ROWS * 4, &full[w][st]);
+        };
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < min(nblk, RS_STAGES); ++k) issue(k, done + k);
+        // reach head
+        T acc = 0;
+        if (live) {
+            T v[8];
+            acc = __ldcg(A + (size_t)c0 * ld + j);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = q < n0 ? __ldcg(A + (size_t)up[q] * ld + j) : (T)0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < n0) acc += v[q];
+            A[(size_t)c0 * ld + j] = acc;
+        }
+        for (int k = 0; k < nblk; ++k) {
+            const int pos = done + k, st = pos % RS_STAGES;
+            mbar_wait(&full[w][st], (pos / RS_STAGES) & 1);
+            const int base = (b0 + k) * RS_ROWS;
+            const int lo = max(rbeg - base, 0), hi = min(rend - base, RS_ROWS);
+#pragma unroll
+            for (int r = 0; r < RS_ROWS; ++r) {
+                if (r >= lo && r < hi) {
+                    acc += sbuf[w][st][r][lane];
+                    const int32_t c = scell[w][st][r];
+                    if (c >= 0 && live) A[(size_t)c * ld + j] = acc;
+                }
+            }
+            __syncwarp();
+            if (k + RS_STAGES < nblk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(k + RS_STAGES, pos + RS_STAGES);
+            }
+        }
+        done += nblk;
+    }
+}
+
 // dataflow tail: cells order[begin, end) are claimed in order, one ticket per sub-warp group and
 // CHUNK cells per ticket; a cell waits only for tail upstream cells (tailmask) to publish their
 // epoch in done[], which are always held by earlier tickets => no deadlock.
@@ -750,6 +1080,13 @@ struct wfa_plan {
     int comp_level = 0, ncomp = 0, nupper = 0;
     bool comp_ok = false;
     DevBuf corder, cmask, cnext, comps, cup_off, cup_idx;
+    // upper network regrouped by river reach (see k_reach_sweep)
+    bool run_ok = false;
+    int run_critical = 0;
+    int nruns = 0;
+    DevBuf rcell, rup_off, rup_idx, run_start, row_off, rowcell, rstream, rinfo;
+    int nrows = 0;
+    std::vector<int32_t> h_rlv_off;      // first reach of every reach level
 };
 
 static void plan_free(wfa_plan *p)
@@ -758,7 +1095,8 @@ static void plan_free(wfa_plan *p)
     cudaSetDevice(p->device);
     DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
-                      &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx};
+                      &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx, &p->rcell, &p->rup_off,
+                      &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo};
     for (DevBuf *d : bufs) d->release();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -768,6 +1106,7 @@ static void plan_free(wfa_plan *p)
 }
 
 static int plan_build_components(wfa_plan *p);
+static int plan_build_runs(wfa_plan *p);
 
 static int plan_build(wfa_plan *p, const int16_t *dir_dev)
 {
@@ -979,6 +1318,156 @@ static int plan_build_components(wfa_plan *p)
     cleanup();
 #undef QCK
 #undef QRC
+    return plan_build_runs(p);
+}
+
+
+// Regroup the upper network (levels >= comp_level) by river reach; see k_reach_sweep.
+static int plan_build_runs(wfa_plan *p)
+{
+    p->run_ok = false;
+    const std::vector<int32_t> &off = p->h_level_off;
+    const int lc = p->comp_level;
+    if (lc >= p->nlevels) return GR2M_OK;
+    const int ub = off[lc], nu = p->norder - ub;
+    if (nu <= 0 || nu >= (1 << 28)) return GR2M_OK;
+    cudaStream_t st = p->stream;
+    const long long n = p->ncell;
+    const int nb = ceil_div(nu, 256);
+    const int32_t *uorder = p->order.as<int32_t>() + ub;
+    DevBuf upos, pred, npu, h0, h1, d0, d1, rl, flag, keys, keys2, vals, sj, temp, isstart, rank, cnt, runrl;
+    auto cleanup = [&]() {
+        DevBuf *t[] = {&upos, &pred, &npu, &h0, &h1, &d0, &d1, &rl, &flag, &keys, &keys2, &vals, &sj, &temp, &isstart,
+                       &rank, &cnt, &runrl};
+        for (DevBuf *d : t) d->release();
+    };
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+#define RRC(call) do { int r_ = (call); if (r_) { cleanup(); return r_; } } while (0)
+    RRC(upos.ensure(n * 4));
+    RRC(pred.ensure((size_t)nu * 4));
+    RRC(npu.ensure(nu));
+    RRC(h0.ensure((size_t)nu * 4));
+    RRC(h1.ensure((size_t)nu * 4));
+    RRC(d0.ensure((size_t)nu * 4));
+    RRC(d1.ensure((size_t)nu * 4));
+    RRC(rl.ensure((size_t)nu * 4));
+    RRC(flag.ensure(sizeof(int)));
+    k_run_upos<<<nb, 256, 0, st>>>(uorder, nu, upos.as<int32_t>());
+    k_run_pred<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
+                                   upos.as<int32_t>(), pred.as<int32_t>(), npu.as<uint8_t>());
+    k_run_rank_init<<<nb, 256, 0, st>>>(pred.as<int32_t>(), nu, h0.as<int32_t>(), d0.as<int32_t>());
+    RCK(cudaGetLastError());
+    int32_t *hs = h0.as<int32_t>(), *hd = h1.as<int32_t>(), *ds = d0.as<int32_t>(), *dd = d1.as<int32_t>();
+    int changed = 1;
+    for (int it = 0; changed && it < 40; ++it) {
+        RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        k_run_rank_step<<<nb, 256, 0, st>>>(hs, ds, nu, hd, dd, flag.as<int>());
+        RCK(cudaGetLastError());
+        RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RCK(cudaStreamSynchronize(st));
+        std::swap(hs, hd);
+        std::swap(ds, dd);
+    }
+    // reach levels
+    RCK(cudaMemsetAsync(rl.p, 0, (size_t)nu * 4, st));
+    changed = 1;
+    int nrl_iter = 0;
+    for (; changed && nrl_iter < 100000; ++nrl_iter) {
+        RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        k_run_level_step<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
+                                             upos.as<int32_t>(), hs, npu.as<uint8_t>(), rl.as<int32_t>(), flag.as<int>());
+        RCK(cudaGetLastError());
+        RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RCK(cudaStreamSynchronize(st));
+    }
+    if (nrl_iter >= 65000) { cleanup(); return GR2M_OK; }     // does not fit the sort key: keep the other sweeps
+    // sort by (reach level, reach head, position in reach)
+    RRC(keys.ensure((size_t)nu * 8));
+    RRC(keys2.ensure((size_t)nu * 8));
+    RRC(vals.ensure((size_t)nu * 4));
+    RRC(sj.ensure((size_t)nu * 4));
+    k_run_keys<<<nb, 256, 0, st>>>(hs, ds, rl.as<int32_t>(), nu, keys.as<unsigned long long>(), vals.as<int32_t>());
+    RCK(cudaGetLastError());
+    size_t tbytes = 0;
+    RCK(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
+                                        vals.as<int32_t>(), sj.as<int32_t>(), nu, 0, 64, st));
+    RRC(temp.ensure(tbytes ? tbytes : 16));
+    RCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
+                                        vals.as<int32_t>(), sj.as<int32_t>(), nu, 0, 64, st));
+    RRC(p->rcell.ensure((size_t)nu * 4));
+    RRC(p->rup_off.ensure(((size_t)nu + 1) * 4));
+    RRC(isstart.ensure((size_t)nu * 4));
+    RRC(rank.ensure((size_t)nu * 4));
+    RRC(cnt.ensure((size_t)nu * 4));
+    k_run_gather<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, uorder, ds, p->inmask.as<uint8_t>(), p->rcell.as<int32_t>(),
+                                     isstart.as<int32_t>(), cnt.as<int32_t>());
+    RCK(cudaGetLastError());
+    size_t sbytes = 0;
+    RCK(cub::DeviceScan::InclusiveSum(nullptr, sbytes, cnt.as<int32_t>(), p->rup_off.as<int32_t>() + 1, nu, st));
+    if (sbytes > temp.cap) RRC(temp.ensure(sbytes));
+    RCK(cudaMemsetAsync(p->rup_off.p, 0, 4, st));
+    RCK(cub::DeviceScan::InclusiveSum(temp.p, sbytes, cnt.as<int32_t>(), p->rup_off.as<int32_t>() + 1, nu, st));
+    RCK(cub::DeviceScan::InclusiveSum(nullptr, sbytes, isstart.as<int32_t>(), rank.as<int32_t>(), nu, st));
+    if (sbytes > temp.cap) RRC(temp.ensure(sbytes));
+    RCK(cub::DeviceScan::InclusiveSum(temp.p, sbytes, isstart.as<int32_t>(), rank.as<int32_t>(), nu, st));
+    int nedges = 0, nr = 0;
+    RCK(cudaMemcpyAsync(&nedges, p->rup_off.as<int32_t>() + nu, 4, cudaMemcpyDeviceToHost, st));
+    RCK(cudaMemcpyAsync(&nr, rank.as<int32_t>() + (nu - 1), 4, cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    if (nr <= 0) { cleanup(); return GR2M_OK; }
+    RRC(p->rup_idx.ensure(std::max<size_t>(16, (size_t)nedges * 4)));
+    RRC(p->run_start.ensure(((size_t)nr + 1) * 4));
+    RRC(runrl.ensure((size_t)nr * 4));
+    k_run_starts<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), rank.as<int32_t>(), nu, p->run_start.as<int32_t>());
+    RCK(cudaMemcpyAsync(p->run_start.as<int32_t>() + nr, &nu, 4, cudaMemcpyHostToDevice, st));
+    k_run_upfill<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, p->ncol, p->rcell.as<int32_t>(), p->inmask.as<uint8_t>(),
+                                     pred.as<int32_t>(), uorder, p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>());
+    // the reach stream: rows per cell, their offsets, and which cell completes at which row
+    RRC(p->row_off.ensure(((size_t)nu + 1) * 4));
+    k_run_rows<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(), nu,
+                                   cnt.as<int32_t>());
+    RCK(cudaGetLastError());
+    RCK(cub::DeviceScan::InclusiveSum(nullptr, sbytes, cnt.as<int32_t>(), p->row_off.as<int32_t>() + 1, nu, st));
+    if (sbytes > temp.cap) RRC(temp.ensure(sbytes));
+    RCK(cudaMemsetAsync(p->row_off.p, 0, 4, st));
+    RCK(cub::DeviceScan::InclusiveSum(temp.p, sbytes, cnt.as<int32_t>(), p->row_off.as<int32_t>() + 1, nu, st));
+    int nrows = 0;
+    RCK(cudaMemcpyAsync(&nrows, p->row_off.as<int32_t>() + nu, 4, cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    RRC(p->rowcell.ensure(((size_t)nrows + 2 * RS_ROWS) * 4));        // the sweep copies whole RS_ROWS blocks
+    RCK(cudaMemsetAsync(p->rowcell.p, 0xff, ((size_t)nrows + 2 * RS_ROWS) * 4, st));
+    k_run_rowcell<<<nb, 256, 0, st>>>(p->row_off.as<int32_t>(), p->rcell.as<int32_t>(), nu, p->rowcell.as<int32_t>());
+    RRC(p->rinfo.ensure((size_t)nr * 48));
+    k_run_pack<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, p->rcell.as<int32_t>(),
+                                                 p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(),
+                                                 p->row_off.as<int32_t>(), p->rinfo.as<int4>());
+    p->nrows = nrows;
+    k_run_levels<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, sj.as<int32_t>(), rl.as<int32_t>(),
+                                                   runrl.as<int32_t>());
+    RCK(cudaGetLastError());
+    std::vector<int32_t> hrl(nr);
+    RCK(cudaMemcpyAsync(hrl.data(), runrl.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    p->h_rlv_off.clear();
+    for (int r = 0; r < nr; ++r)
+        if (r == 0 || hrl[r] != hrl[r - 1]) p->h_rlv_off.push_back(r);      // reaches are sorted by level
+    p->h_rlv_off.push_back(nr);
+    {   // latency chain of the level-synchronous reach sweep: longest reach of every level, summed
+        std::vector<int32_t> hs(nr + 1);
+        RCK(cudaMemcpy(hs.data(), p->run_start.p, ((size_t)nr + 1) * 4, cudaMemcpyDeviceToHost));
+        long long crit = 0;
+        for (size_t l = 0; l + 1 < p->h_rlv_off.size(); ++l) {
+            int mx = 0;
+            for (int r = p->h_rlv_off[l]; r < p->h_rlv_off[l + 1]; ++r) mx = std::max(mx, hs[r + 1] - hs[r]);
+            crit += mx;
+        }
+        p->run_critical = (int)std::min<long long>(crit, INT32_MAX);
+    }
+    p->nruns = nr;
+    p->run_ok = true;
+    cleanup();
+#undef RCK
+#undef RRC
     return GR2M_OK;
 }
 
@@ -1066,6 +1555,17 @@ extern "C" int wfa_plan_basin_info(const wfa_plan *p, int *cut_level, int *nbasi
     return GR2M_OK;
 }
 
+extern "C" int wfa_plan_reach_info(const wfa_plan *p, int *nreaches, int *nreach_levels, int *critical_cells,
+                                   int *enabled)
+{
+    REQUIRE(p != nullptr, "plan is NULL");
+    if (nreaches) *nreaches = p->run_ok ? p->nruns : 0;
+    if (nreach_levels) *nreach_levels = p->run_ok ? (int)p->h_rlv_off.size() - 1 : 0;
+    if (critical_cells) *critical_cells = p->run_ok ? p->run_critical : 0;
+    if (enabled) *enabled = p->run_ok ? 1 : 0;
+    return GR2M_OK;
+}
+
 extern "C" int wfa_plan_export(const wfa_plan *pc, int32_t *receiver, uint8_t *inmask, int32_t *indeg, int32_t *level,
                                int32_t *order, int32_t *level_off, uint8_t *contam)
 {
@@ -1113,10 +1613,11 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     const std::vector<int32_t> &off = p->h_level_off;
     const int gpb = 256 / G;   // lane groups per 256-thread block
     const bool dataflow = (flags & WFA_DATAFLOW) != 0;
-    const bool by_basin = p->comp_ok && !dataflow && !(flags & WFA_LEVEL_SYNC);
+    const bool by_reach = p->run_ok && !dataflow && !(flags & (WFA_LEVEL_SYNC | WFA_BY_BASIN));
+    const bool by_basin = p->comp_ok && !dataflow && !(flags & WFA_LEVEL_SYNC) && !by_reach;
     // the thin tail starts where every later level fits a few passes of the single resident CTA
     int l0 = p->tail_level;
-    if (by_basin) {
+    if (by_basin || by_reach) {
         l0 = p->comp_level;
     } else if (!dataflow) {
         const int width = 4 * (1024 / G);
@@ -1131,7 +1632,23 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->evm, st));
     if (l0 < p->nlevels) {
-        if (by_basin) {
+        if (by_reach) {
+            const int nu = p->norder - off[p->comp_level];
+            const int lds = (nmonth + 3) & ~3;    // stream rows are multiples of 16 bytes for the bulk copies
+            {
+                int rc_ = p->rstream.ensure(((size_t)p->nrows + 2 * RS_ROWS) * lds * sizeof(T));
+                if (rc_) return rc_;
+            }
+            T *S = p->rstream.as<T>();
+            k_reach_gather<T, G><<<ceil_div(nu, gpb), 256, 0, st>>>(p->rcell.as<int32_t>(), p->rup_off.as<int32_t>(),
+                                                                    p->rup_idx.as<uint32_t>(), p->row_off.as<int32_t>(), nu,
+                                                                    A, S, ld, lds, nmonth);
+            for (size_t l = 0; l + 1 < p->h_rlv_off.size(); ++l) {
+                const int r0 = p->h_rlv_off[l], r1 = p->h_rlv_off[l + 1];
+                k_reach_sweep<T><<<ceil_div(r1 - r0, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
+                    p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), r0, r1, S, lds, A, ld, nmonth);
+            }
+        } else if (by_basin) {
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
             int blocks = std::min(p->ncomp, 148 * 7);
             if (G >= 16 && nmonth <= G && !(flags & WFA_NO_FORWARD))

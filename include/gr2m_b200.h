@@ -57,6 +57,8 @@ extern "C" {
 #define WFA_LEVEL_SYNC        4   /* sweep the upper levels grid-wide (one launch / one CTA per level) instead of
                                      per outlet basin, which is the default when the forest splits well */
 #define WFA_DATAFLOW          8   /* flag-driven dataflow kernel for the thin tail instead */
+#define WFA_BY_BASIN          32   /* sweep the upper levels per outlet basin (level by level inside a CTA) instead of per
+                                      river reach, the default */
 #define WFA_NO_FORWARD        16   /* per-basin sweep without shared-memory forwarding of fresh rows (A/B switch) */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
@@ -138,6 +140,10 @@ int wfa_plan_info(const wfa_plan *p, int *nlevels, int *norder, int64_t *ncell);
 /* per-outlet-basin regrouping of the upper levels: cut level, number of basins (trees), cells above the
  * cut, and whether the sweep uses it (it needs >= 32 basins, none holding more than 1/8 of those cells) */
 int wfa_plan_basin_info(const wfa_plan *p, int *cut_level, int *nbasins, int *nupper, int *enabled);
+/* River reaches of the same upper network: maximal chains of cells with one upper inflow each, swept by one lane
+ * group per reach, reaches grouped into `nreach_levels` dependency levels (one launch each);
+ * `critical_cells` = sum over those levels of the longest reach, the sweep's serial chain in cells. */
+int wfa_plan_reach_info(const wfa_plan *p, int *nreaches, int *nreach_levels, int *critical_cells, int *enabled);
 /* Copy the integer topology back (any pointer may be NULL): receiver/indeg/level [ncell] int32,
  * inmask/contam [ncell] uint8, order [norder], level_off [nlevels+1]. */
 int wfa_plan_export(const wfa_plan *p, int32_t *receiver, uint8_t *inmask, int32_t *indeg,

@@ -8,7 +8,7 @@ from gr2msemidistr_b200 import capi, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=8000)
 ap.add_argument("--batches", default="16,32")
-ap.add_argument("--flags", default="0,8")
+ap.add_argument("--flags", default="0,32,4")
 a = ap.parse_args()
 g.build(); capi.set_device(0)
 dev = torch.device("cuda", 0)
@@ -17,17 +17,21 @@ d8 = synth.d8_grid(a.n, a.n, device=dev); torch.cuda.synchronize()
 t0 = time.perf_counter(); plan = capi.Plan(dev_ptr=d8.data_ptr(), shape=(a.n, a.n)); t_plan = time.perf_counter() - t0
 del d8
 plan.set_stream(st.cuda_stream)
-print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan, "basins": plan.basin_info()}), flush=True)
+print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan, "basins": plan.basin_info(), "reaches": plan.reach_info()}), flush=True)
 for ld in [int(x) for x in a.batches.split(",")]:
     A = torch.empty((a.n * a.n, ld), dtype=torch.float64, device=dev)
     for fl in [int(x) for x in a.flags.split(",")]:
         best = 1e30
         for rep in range(3):
-            A.uniform_(0.0, 100.0)
+            torch.manual_seed(1); A.uniform_(0.0, 100.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); plan.accumulate_dev(A.data_ptr(), ld, ld, fl); e1.record(); e1.synchronize()
             if e0.elapsed_time(e1) < best:
                 best, phases = e0.elapsed_time(e1), plan.last_phase_ms()
+        if fl == int(a.flags.split(",")[0]):
+            ref = int(A.view(torch.int64).sum())        # wrap-around sum of the bit patterns
+        else:
+            assert int(A.view(torch.int64).sum()) == ref, "sweeps differ"
         units = a.n * a.n * ld
         print(json.dumps({"ld": ld, "flags": fl, "ms": best, "wide_ms": phases[0], "tail_ms": phases[1], "cell_months_per_s": units / best * 1e3,
                           "GBps_algorithmic": units * 16 / best * 1e3 / 1e9}), flush=True)

@@ -47,7 +47,7 @@ def test_plan_edge_cases(capi, oracle, rng):
             for k in PLAN_KEYS:
                 assert np.array_equal(got[k], ref[k]), k
             W = rng.uniform(0, 10, (3,) + d.shape)
-            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC):
+            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN):
                 A = p.accumulate(W, fl)
                 Ar = np.stack([oracle.aread8(d, W[m], contcheck=not (fl & capi.WFA_NO_CONTAMINATION)) for m in range(3)])
                 assert np.array_equal(np.isnan(A), np.isnan(Ar))
@@ -59,7 +59,7 @@ def test_accumulate_dense_matches_oracle(capi, oracle, rng, nmonth):
     d = synth.d8_grid(150, 210, seed=7).numpy()
     W = rng.uniform(0, 100, (nmonth, 150, 210))
     with capi.Plan(d) as p:
-        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_NO_CONTAMINATION):
+        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN, capi.WFA_NO_CONTAMINATION):
             A = p.accumulate(W, fl)
             cc = not (fl & capi.WFA_NO_CONTAMINATION)
             for m in {0, nmonth // 2, nmonth - 1}:
@@ -157,21 +157,22 @@ def test_route_edge_cases(capi, oracle, rng):
 
 
 def test_per_basin_sweep_is_used_and_bit_identical(capi, oracle, rng):
-    # a grid that splits into many outlet basins: the default sweep regroups the upper levels by basin;
+    # a grid that splits into many outlet basins: WFA_BY_BASIN regroups the upper levels by basin;
     # it must give the same bits as the grid-wide level sweep and as the oracle
     nrow, ncol = 900, 1200
     d = synth.d8_grid(nrow, ncol, seed=5).numpy()
     W = rng.uniform(0, 100, (33, nrow, ncol))
+    NC, BB = capi.WFA_NO_CONTAMINATION, capi.WFA_BY_BASIN
     with capi.Plan(d) as p:
         info = p.basin_info()
         assert info["enabled"] and info["nbasins"] >= 32 and info["nupper"] > 0
-        A = p.accumulate(W, capi.WFA_NO_CONTAMINATION)
-        B = p.accumulate(W, capi.WFA_NO_CONTAMINATION | capi.WFA_LEVEL_SYNC)
+        A = p.accumulate(W, NC | BB)
+        B = p.accumulate(W, NC | capi.WFA_LEVEL_SYNC)
         # 32 and 20 months take the shared-memory-forwarding kernel (nmonth <= lanes per cell), 33 the general one
-        C32 = p.accumulate(W[:32], capi.WFA_NO_CONTAMINATION)
-        D32 = p.accumulate(W[:32], capi.WFA_NO_CONTAMINATION | capi.WFA_NO_FORWARD)
-        C20 = p.accumulate(W[:20], capi.WFA_NO_CONTAMINATION | capi.WFA_F32)
-        D20 = p.accumulate(W[:20], capi.WFA_NO_CONTAMINATION | capi.WFA_F32 | capi.WFA_LEVEL_SYNC)
+        C32 = p.accumulate(W[:32], NC | BB)
+        D32 = p.accumulate(W[:32], NC | BB | capi.WFA_NO_FORWARD)
+        C20 = p.accumulate(W[:20], NC | BB | capi.WFA_F32)
+        D20 = p.accumulate(W[:20], NC | capi.WFA_F32 | capi.WFA_LEVEL_SYNC)
     assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(B, nan=-1))
     assert np.array_equal(np.nan_to_num(C32, nan=-1), np.nan_to_num(A[:32], nan=-1))
     assert np.array_equal(np.nan_to_num(D32, nan=-1), np.nan_to_num(A[:32], nan=-1))
@@ -179,6 +180,31 @@ def test_per_basin_sweep_is_used_and_bit_identical(capi, oracle, rng):
     for m in (0, 32):
         Ar = oracle.aread8(d, W[m], contcheck=False)
         assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(Ar, nan=-1))
+
+
+@pytest.mark.parametrize("width", [0, 64])
+def test_reach_sweep_is_used_and_bit_identical(capi, oracle, rng, width, monkeypatch):
+    # default sweep of the upper network: one lane group per river reach, reaches in dependency levels.
+    # Same k-ordered additions as every other sweep => same bits.  width=64 moves the cut far down so
+    # that the reach network has many confluences and short reaches.
+    if width:
+        monkeypatch.setenv("WFA_COMP_WIDTH", str(width))
+    nrow, ncol = 700, 1100
+    d = synth.d8_grid(nrow, ncol, seed=11).numpy()
+    NC = capi.WFA_NO_CONTAMINATION
+    with capi.Plan(d) as p:
+        ri = p.reach_info()
+        assert ri["enabled"] and ri["nreaches"] > 0 and 0 < ri["nreach_levels"] < p.nlevels
+        for nm, fl in ((33, 0), (32, 0), (7, 0), (1, 0), (20, capi.WFA_F32), (40, capi.WFA_F32)):
+            W = rng.uniform(0, 100, (nm, nrow, ncol))
+            A = p.accumulate(W, NC | fl)
+            B = p.accumulate(W, NC | fl | capi.WFA_LEVEL_SYNC)
+            assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(B, nan=-1)), (nm, fl)
+        W = rng.uniform(0, 100, (3, nrow, ncol))
+        A = p.accumulate(W, 0)
+        for m in range(3):
+            Ar = oracle.aread8(d, W[m], contcheck=True)
+            assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(Ar, nan=-1))
 
 
 def test_linearity_and_mass_conservation_large(capi, rng):
