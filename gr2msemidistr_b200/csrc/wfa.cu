@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
                                                               const T *__restrict__ S, int lds, T *A, int ld,
                                                               int nmonth)
 {
-    __shared__ alignas(128) T sbuf[RS_WARPS][RS_STAGES][RS_ROWS][32];
+    __shared__ alignas(128) T sbuf[RS_WARPS][RS_STAGES][RS_ROWS * 32];
     __shared__ alignas(16) int32_t scell[RS_WARPS][RS_STAGES][RS_ROWS];
     __shared__ alignas(8) uint64_t full[RS_WARPS][RS_STAGES];
     const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -877,21 +877,33 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
     const int rbeg = h0.x, rend = h0.y, c0 = h0.z, n0 = h0.w;
     const int up[8] = {h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w};
     const int b0 = rbeg / RS_ROWS, nblk = rend > rbeg ? (rend + RS_ROWS - 1) / RS_ROWS - b0 : 0;
+    // rows narrower than 32 values are contiguous in the stream: one copy per stage, row pitch lds in
+    // shared memory too; wider rows are swept 32 months at a time, one copy per row
+    const bool dense = lds <= 32;
+    const int spitch = dense ? lds : 32;
+    const size_t apitch = (size_t)ld * sizeof(T);
     int done = 0;                                 // stream blocks consumed so far over all passes (ring position)
     for (int j0 = 0; j0 < nmonth; j0 += 32) {
         const int j = j0 + lane;
         const bool live = j < nmonth;
+        char *Aj = reinterpret_cast<char *>(A + (live ? j : 0));
         const uint32_t segbytes = (uint32_t)min(32, lds - j0) * (uint32_t)sizeof(T);
-        auto issue = [&](int k, int pos) {        // stream block b0+k into ring slot pos % RS_STAGES
+        auto issue = [&](int k, int pos) {        // stream block b0+k into ring slot pos % RS_STAGES (lane 0 only)
             const int st = pos % RS_STAGES;
             const size_t row = (size_t)(b0 + k) * RS_ROWS;
-            if (lane == 0) mbar_arrive_expect_tx(&full[w][st], RS_ROWS * segbytes + RS_ROWS * 4);
-            __syncwarp();
-            if (lane < RS_ROWS) bulk_g2s(&sbuf[w][st][lane][0], S + (row + lane) * lds + j0, segbytes, &full[w][st]);
-            if (lane == RS_ROWS) bulk_g2s(&scell[w][st][0], rowcell + row, RS_ROWS * 4, &full[w][st]);
+            mbar_arrive_expect_tx(&full[w][st], RS_ROWS * segbytes + RS_ROWS * 4);
+            if (dense) {
+                bulk_g2s(&sbuf[w][st][0], S + row * lds, RS_ROWS * segbytes, &full[w][st]);
+            } else {
+                for (int r = 0; r < RS_ROWS; ++r)
+                    bulk_g2s(&sbuf[w][st][r * 32], S + (row + r) * lds + j0, segbytes, &full[w][st]);
+            }
+            bulk_g2s(&scell[w][st][0], rowcell + row, RS_ROWS * 4, &full[w][st]);
         };
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int k = 0; k < min(nblk, RS_STAGES); ++k) issue(k, done + k);
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int k = 0; k < min(nblk, RS_STAGES); ++k) issue(k, done + k);
+        }
         // reach head
         T acc = 0;
         if (live) {
@@ -909,16 +921,25 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
             mbar_wait(&full[w][st], (pos / RS_STAGES) & 1);
             const int base = (b0 + k) * RS_ROWS;
             const int lo = max(rbeg - base, 0), hi = min(rend - base, RS_ROWS);
+            const T *sb = &sbuf[w][st][lane];
+            const int4 *sc = reinterpret_cast<const int4 *>(&scell[w][st][0]);
+            auto step = [&](T v, int32_t c) {
+                acc += v;
+                if (c >= 0 && live) *reinterpret_cast<T *>(Aj + (size_t)c * apitch) = acc;
+            };
+            if (lo == 0 && hi == RS_ROWS) {
 #pragma unroll
-            for (int r = 0; r < RS_ROWS; ++r) {
-                if (r >= lo && r < hi) {
-                    acc += sbuf[w][st][r][lane];
-                    const int32_t c = scell[w][st][r];
-                    if (c >= 0 && live) A[(size_t)c * ld + j] = acc;
+                for (int q = 0; q < RS_ROWS / 4; ++q) {
+                    const int4 c4 = sc[q];
+                    const T v0 = sb[(4 * q + 0) * spitch], v1 = sb[(4 * q + 1) * spitch],
+                            v2 = sb[(4 * q + 2) * spitch], v3 = sb[(4 * q + 3) * spitch];
+                    step(v0, c4.x); step(v1, c4.y); step(v2, c4.z); step(v3, c4.w);
                 }
+            } else {
+                for (int r = lo; r < hi; ++r) step(sb[r * spitch], scell[w][st][r]);
             }
             __syncwarp();
-            if (k + RS_STAGES < nblk) {
+            if (lane == 0 && k + RS_STAGES < nblk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(k + RS_STAGES, pos + RS_STAGES);
             }
