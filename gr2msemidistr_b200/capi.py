@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgr2m_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4
 PERC_F32_EXPONENT, SINK_UNROUNDED, MATH_LITERAL = 1, 8, 16
 OF_KGE, OF_NSE, OF_RMSE = 0, 1, 2
-WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW, WFA_NO_FORWARD, WFA_BY_BASIN = 1, 2, 4, 8, 16, 32
+WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW, WFA_NO_FORWARD, WFA_BY_BASIN, WFA_ROUTE_DENSE = 1, 2, 4, 8, 16, 32, 64
 OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
@@ -27,7 +27,8 @@ SYMBOLS = (
     "gr2m_basin_create", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
-    "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
+    "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_router_create", "wfa_router_destroy",
+    "wfa_router_info", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
     "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem",
 )
 
@@ -167,6 +168,55 @@ class Basin:
                                               C.c_void_p(of_ptr), C.c_void_p(crit_ptr or 0), C.c_void_p(qt_ptr or 0)))
 
 
+class Router:
+    """wfa_router handle: the routing operator of one (D8 plan, source cells, polygons) geometry.
+
+    apply(QS) gives what Plan.route(QS, ...) gives, for any number of columns (months, or months x sets)."""
+
+    def __init__(self, plan: "Plan", src_cell, poly_off, poly_cells, flags: int = 0):
+        self._h = C.c_void_p()
+        self._plan = plan                      # the router borrows the plan's topology and stream
+        src, poff, pc = _i32(src_cell), _i32(poly_off), _i32(poly_cells)
+        self.nsub = int(src.shape[0])
+        if poff.shape != (self.nsub + 1,):
+            raise ValueError("src_cell must be [nsub], poly_off [nsub+1]")
+        if pc.size == 0:
+            pc = np.zeros(1, np.int32)
+        _check(lib().wfa_router_create(plan._h, C.c_int(self.nsub), _ip(src), _ip(poff), _ip(pc), C.c_int(flags),
+                                       C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.wfa_router_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        _check(lib().wfa_router_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(nnodes=a.value, nlevels=b.value, ncandidates=c.value, nactive=d.value)
+
+    def apply(self, QS):
+        """QS [nsub, ncols] -> QR [nsub, ncols] (unrounded per-polygon maxima)."""
+        QS = _f64(QS)
+        if QS.ndim != 2 or QS.shape[0] != self.nsub:
+            raise ValueError("QS must be [nsub, ncols]")
+        QR = np.empty_like(QS)
+        _check(lib().wfa_router_apply(self._h, C.c_int(QS.shape[1]), _dp(QS), _dp(QR)))
+        return QR
+
+    def apply_dev(self, qs_ptr: int, qr_ptr: int, ncols: int):
+        """Device-resident, asynchronous on the plan's stream: QS, QR are [nsub][ncols] FP64 in HBM."""
+        _check(lib().wfa_router_apply_dev(self._h, C.c_int(ncols), C.c_void_p(qs_ptr), C.c_void_p(qr_ptr)))
+
+
 def run_once(P, E, area, ndays, region_id, nreg, params, S0=None, R0=None, flags=0):
     """gr2m_run_once: create + run + destroy through the single C entry point."""
     P, E = _f64(P), _f64(E)
@@ -261,6 +311,10 @@ class Plan:
         _check(lib().wfa_route(self._h, C.c_int(ntime), C.c_int(nsub), _dp(QS), _ip(src), _ip(poff), _ip(pc),
                                C.c_int(flags), _dp(QR)))
         return QR
+
+    def router(self, src_cell, poly_off, poly_cells, flags: int = 0):
+        """Month-invariant routing operator for these source cells and polygons (see Router)."""
+        return Router(self, src_cell, poly_off, poly_cells, flags)
 
     def accumulate(self, W, flags: int = 0):
         """Dense AreaD8 -wg.  W [nmonth, nrow, ncol] (or [nrow, ncol]) -> A of the same shape, NaN = nodata."""

@@ -15,6 +15,7 @@
 // upper levels are swept grid-wide instead: one launch per level, then a single resident CTA for the
 // long thin tail (WFA_LEVEL_SYNC), or a ticketed flag-driven dataflow kernel (WFA_DATAFLOW).
 #include "common.cuh"
+#include "wfa_plan.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1087,28 +1088,6 @@ constexpr int TAIL_WIDTH = 512;       // dataflow sweep: the tail starts where e
 
 }  // namespace
 
-struct wfa_plan {
-    int device = 0, nrow = 0, ncol = 0, nlevels = 0, norder = 0, tail_level = 0, flags = 0;
-    long long ncell = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;   // start, end, end of the wide-level phase
-    bool timed = false;
-    unsigned epoch = 0;
-    DevBuf receiver, inmask, omask, indeg, level, order, level_off, contam, tailmask, done, ticket, work, work2, qs, src, poff,
-        pcells, qr;
-    std::vector<int32_t> h_level_off;
-    // upper forest regrouped by outlet basin (see k_accum_components)
-    int comp_level = 0, ncomp = 0, nupper = 0;
-    bool comp_ok = false;
-    DevBuf corder, cmask, cnext, comps, cup_off, cup_idx;
-    // upper network regrouped by river reach (see k_reach_sweep)
-    bool run_ok = false;
-    int run_critical = 0;
-    int nruns = 0;
-    DevBuf rcell, rup_off, rup_idx, run_start, row_off, rowcell, rstream, rinfo;
-    int nrows = 0;
-    std::vector<int32_t> h_rlv_off;      // first reach of every reach level
-};
 
 static void plan_free(wfa_plan *p)
 {
@@ -1780,6 +1759,15 @@ extern "C" int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, con
     const int npc = poly_off[nsub];
     for (int q = 0; q < npc; ++q) REQUIRE(poly_cells[q] >= 0 && poly_cells[q] < n, "poly_cells out of range");
     CK(cudaSetDevice(p->device));
+    if (!(flags & WFA_ROUTE_DENSE) && n < (1ll << 30)) {
+        // weights sit at nsub cells only: build the month-invariant operator and apply it to all months
+        wfa_router *r = nullptr;
+        int rc = wfa_router_create(p, nsub, src_cell, poly_off, poly_cells, flags, &r);
+        if (rc) return rc;
+        rc = wfa_router_apply(r, ntime, QS, QR);
+        wfa_router_destroy(r);
+        return rc;
+    }
     // duplicates: the last assignment wins, as R's `[<-` (Routing:109-113)
     std::vector<int32_t> src(src_cell, src_cell + nsub);
     {

@@ -59,6 +59,8 @@ extern "C" {
 #define WFA_DATAFLOW          8   /* flag-driven dataflow kernel for the thin tail instead */
 #define WFA_BY_BASIN          32   /* sweep the upper levels per outlet basin (level by level inside a CTA) instead of per
                                       river reach, the default */
+#define WFA_ROUTE_DENSE       64   /* wfa_route: sweep the whole grid month by month (as AreaD8 does) instead of
+                                      applying the month-invariant routing operator, the default */
 #define WFA_NO_FORWARD        16   /* per-basin sweep without shared-memory forwarding of fresh rows (A/B switch) */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
@@ -157,6 +159,21 @@ int wfa_plan_export(const wfa_plan *p, int32_t *receiver, uint8_t *inmask, int32
  *             the wrapper applies round(,1) (Routing:131). */
 int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, const int32_t *src_cell,
               const int32_t *poly_off, const int32_t *poly_cells, int flags, double *QR);
+
+/* Month-invariant routing operator (same inputs and result as wfa_route, split in two): everything that
+ * depends on the D8 grid, the source cells and the polygons only is computed once; applying it costs
+ * O(confluences of source-carrying paths) per column instead of O(grid cells).  QS and QR are
+ * [ncols x nsub] column-major; the columns are months, or months x parameter sets alike.  `flags` takes
+ * WFA_F32 and WFA_NO_CONTAMINATION.  Results equal the dense sweep's bit for bit (a zero may differ in sign). */
+typedef struct wfa_router wfa_router;
+int wfa_router_create(wfa_plan *p, int nsub, const int32_t *src_cell, const int32_t *poly_off,
+                      const int32_t *poly_cells, int flags, wfa_router **out);
+void wfa_router_destroy(wfa_router *r);
+/* nnodes: sources + confluences; nlevels: evaluation levels (launches per apply); ncandidates: summed
+ * length of the per-polygon node lists; nactive: grid cells at or below a source. */
+int wfa_router_info(const wfa_router *r, int *nnodes, int *nlevels, int *ncandidates, long long *nactive);
+int wfa_router_apply(wfa_router *r, int ncols, const double *QS, double *QR);           /* host buffers */
+int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_dev, double *QR_dev); /* device, async */
 
 /* Dense AreaD8 -wg for nmonth weight grids: W, A are [nmonth][ncell] (month planes, row-major
  * cells).  Nodata / contaminated cells come back as NaN (TauDEM -1 -> NA after raster()). */
