@@ -179,6 +179,36 @@ def cpu_routing(a):
                       f"one month per thread"}
 
 
+def bench_router(a, capi, torch, plan, n, months, dense_ms_one_gpu):
+    """Routing as Routing_GR2MSemiDistr uses it (one value per subbasin, per-polygon maximum): the
+    month-invariant operator built once for the geometry, then applied to all months."""
+    from gr2msemidistr_b200 import synth
+    nb = max(1, min(100, n // 40))
+    src, off, cells = synth.block_polygons(n, n, nb, nb, margin=max(1, n // nb // 4))
+    nsub = src.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t0 = time.perf_counter()
+    router = plan.router(src, off, cells)
+    t_build = time.perf_counter() - t0
+    QS = torch.rand((nsub, months), dtype=torch.float64, device=dev) * 300.0
+    QR = torch.empty_like(QS)
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        router.apply_dev(QS.data_ptr(), QR.data_ptr(), months)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    info = router.info()
+    router.close()
+    return {"workload": f"{nsub} subbasins ({nb} x {nb} blocks) on the same {n} x {n} grid x {months} months, QS resident",
+            "build_s": t_build, "apply_ms": best, "dense_sweep_ms_same_months": dense_ms_one_gpu,
+            "interior_cells": int(off[-1]), **info,
+            "note": "same QR as the dense sweep, bit for bit (tests/test_gpu_router.py); build includes the H2D of the "
+                    "polygon cell lists and is paid once per geometry"}
+
+
 def bench_routing(a, capi, torch, rank, world, dist):
     """Secondary metric: batched WFA sweep, months sharded across ranks (plan replicated)."""
     from gr2msemidistr_b200 import synth
@@ -237,9 +267,15 @@ def bench_routing(a, capi, torch, rank, world, dist):
                                         "1.11 ms (5.6 TB/s) = own row + upstream rows + write, about 17 B per cell-month "
                                         "(profiles/r1_route_ncu_full.txt)"}}
     out["basins"] = plan.basin_info()
-    plan.close()
+    out["reaches"] = plan.reach_info()
     del A
     torch.cuda.empty_cache()
+    if rank == 0:
+        try:
+            out["operator"] = bench_router(a, capi, torch, plan, n, months_total, ms * world)
+        except Exception as ex:       # secondary figure: report, do not lose the sweep number
+            out["operator"] = {"error": repr(ex)}
+    plan.close()
     if rank == 0 and not a.no_cpu:
         out["cpu_baseline"] = cpu_routing(a)
     return out
