@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgr2m_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4
 PERC_F32_EXPONENT, SINK_UNROUNDED, MATH_LITERAL = 1, 8, 16
 OF_KGE, OF_NSE, OF_RMSE = 0, 1, 2
-WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW, WFA_NO_FORWARD, WFA_BY_BASIN, WFA_ROUTE_DENSE = 1, 2, 4, 8, 16, 32, 64
+WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW, WFA_NO_FORWARD, WFA_BY_BASIN, WFA_ROUTE_DENSE, WFA_NO_OVERLAP = 1, 2, 4, 8, 16, 32, 64, 128
 OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)

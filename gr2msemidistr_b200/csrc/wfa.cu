@@ -227,26 +227,34 @@ __device__ __forceinline__ void accum_cell2(int32_t c0, unsigned m0, int32_t c1,
     }
 }
 
-// one wide level per launch, two cells per lane group (cells of a level never feed each other)
+// one wide level per launch, two cells per lane group (cells of a level never feed each other).
+// Launched with programmatic stream serialization: the CTAs of level l+1 may become resident while level
+// l drains; they read their topology and pull their own rows (weights, never written by another level)
+// into L2, and only then wait for level l to complete and be visible (griddepcontrol.wait).
 template <typename T, int G>
 __global__ void __launch_bounds__(256) k_accum_level(const int32_t *__restrict__ order, int begin, int end, int ncol,
-                                                     const uint8_t *__restrict__ omask, T *__restrict__ A, int ld,
-                                                     int nmonth)
+                                                     const uint8_t *__restrict__ omask, T *A, int ld, int nmonth)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, g = threadIdx.x % G;
     const int i = begin + 2 * gid;
-    if (i >= end) return;
-    const int32_t c0 = order[i];
-    const unsigned m0 = omask[i];
-    if (i + 1 < end) {
-        const int32_t c1 = order[i + 1];
-        const unsigned m1 = omask[i + 1];
-        if (m0 && m1) accum_cell2<T, G, false>(c0, m0, c1, m1, g, ncol, A, ld, nmonth);
-        else if (m0) accum_cell<T, G, false>(c0, g, ncol, m0, A, ld, nmonth);
-        else if (m1) accum_cell<T, G, false>(c1, g, ncol, m1, A, ld, nmonth);
-    } else if (m0) {
-        accum_cell<T, G, false>(c0, g, ncol, m0, A, ld, nmonth);
+    int32_t c0 = -1, c1 = -1;
+    unsigned m0 = 0, m1 = 0;
+    if (i < end) {
+        c0 = order[i];
+        m0 = omask[i];
+        if (i + 1 < end) { c1 = order[i + 1]; m1 = omask[i + 1]; }
+        const int rowbytes = nmonth * (int)sizeof(T);
+        if (g * 128 < rowbytes) {
+            if (m0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A + (size_t)c0 * ld) + g * 128));
+            if (m1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A + (size_t)c1 * ld) + g * 128));
+        }
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (i >= end) return;
+    if (m0 && m1) accum_cell2<T, G, true>(c0, m0, c1, m1, g, ncol, A, ld, nmonth);
+    else if (m0) accum_cell<T, G, true>(c0, g, ncol, m0, A, ld, nmonth);
+    else if (m1) accum_cell<T, G, true>(c1, g, ncol, m1, A, ld, nmonth);
 }
 
 // thin levels [lev0, lev1) inside one resident CTA with a block barrier between levels.  The topology
@@ -1625,9 +1633,20 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
         while (l0 > 1 && off[l0] - off[l0 - 1] <= width) --l0;
     }
     // level 0 has no upstream cells: nothing to add
-    for (int l = 1; l < l0; ++l) {
-        int b = off[l], e = off[l + 1];
-        k_accum_level<T, G><<<ceil_div(ceil_div(e - b, 2), gpb), 256, 0, st>>>(order, b, e, p->ncol, omask, A, ld, nmonth);
+    {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = (flags & WFA_NO_OVERLAP) ? 0 : 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        for (int l = 1; l < l0; ++l) {
+            int b = off[l], e = off[l + 1];
+            cfg.gridDim = dim3(ceil_div(ceil_div(e - b, 2), gpb));
+            CK(cudaLaunchKernelEx(&cfg, k_accum_level<T, G>, order, b, e, p->ncol, omask, A, ld, nmonth));
+        }
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->evm, st));

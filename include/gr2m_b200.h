@@ -61,6 +61,7 @@ extern "C" {
                                       river reach, the default */
 #define WFA_ROUTE_DENSE       64   /* wfa_route: sweep the whole grid month by month (as AreaD8 does) instead of
                                       applying the month-invariant routing operator, the default */
+#define WFA_NO_OVERLAP       128   /* launch the wide levels without programmatic stream serialization */
 #define WFA_NO_FORWARD        16   /* per-basin sweep without shared-memory forwarding of fresh rows (A/B switch) */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */

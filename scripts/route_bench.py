@@ -8,7 +8,7 @@ from gr2msemidistr_b200 import capi, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=8000)
 ap.add_argument("--batches", default="16,32")
-ap.add_argument("--flags", default="0,32,4")
+ap.add_argument("--flags", default="0,128")
 a = ap.parse_args()
 g.build(); capi.set_device(0)
 dev = torch.device("cuda", 0)

@@ -47,7 +47,7 @@ def test_plan_edge_cases(capi, oracle, rng):
             for k in PLAN_KEYS:
                 assert np.array_equal(got[k], ref[k]), k
             W = rng.uniform(0, 10, (3,) + d.shape)
-            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN):
+            for fl in (0, capi.WFA_NO_CONTAMINATION, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN, capi.WFA_NO_OVERLAP):
                 A = p.accumulate(W, fl)
                 Ar = np.stack([oracle.aread8(d, W[m], contcheck=not (fl & capi.WFA_NO_CONTAMINATION)) for m in range(3)])
                 assert np.array_equal(np.isnan(A), np.isnan(Ar))
@@ -59,7 +59,7 @@ def test_accumulate_dense_matches_oracle(capi, oracle, rng, nmonth):
     d = synth.d8_grid(150, 210, seed=7).numpy()
     W = rng.uniform(0, 100, (nmonth, 150, 210))
     with capi.Plan(d) as p:
-        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN, capi.WFA_NO_CONTAMINATION):
+        for fl in (0, capi.WFA_DATAFLOW, capi.WFA_LEVEL_SYNC, capi.WFA_BY_BASIN, capi.WFA_NO_OVERLAP, capi.WFA_NO_CONTAMINATION):
             A = p.accumulate(W, fl)
             cc = not (fl & capi.WFA_NO_CONTAMINATION)
             for m in {0, nmonth // 2, nmonth - 1}:
