@@ -165,7 +165,8 @@ int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, const int32_t 
  * depends on the D8 grid, the source cells and the polygons only is computed once; applying it costs
  * O(confluences of source-carrying paths) per column instead of O(grid cells).  QS and QR are
  * [ncols x nsub] column-major; the columns are months, or months x parameter sets alike.  `flags` takes
- * WFA_F32 and WFA_NO_CONTAMINATION.  Results equal the dense sweep's bit for bit (a zero may differ in sign). */
+ * WFA_F32 and WFA_NO_CONTAMINATION.  Results equal the dense sweep's bit for bit (a zero may differ in sign).
+ * A router borrows its plan's topology and stream: destroy it before the plan. */
 typedef struct wfa_router wfa_router;
 int wfa_router_create(wfa_plan *p, int nsub, const int32_t *src_cell, const int32_t *poly_off,
                       const int32_t *poly_cells, int flags, wfa_router **out);
