@@ -263,9 +263,11 @@ def bench_routing(a, capi, torch, rank, world, dist):
            "plan_build_s": t_plan, "grid_gen_s": t_gen,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "traffic": None, "algorithmic_bytes_per_unit": 16, "peak_source": hbm_src,
-                        "traffic_note": "ncu --set full, widest level of an 8000^2 grid x 32 months: 6.2 GB DRAM traffic in "
-                                        "1.11 ms (5.6 TB/s) = own row + upstream rows + write, about 17 B per cell-month "
-                                        "(profiles/r1_route_ncu_full.txt)"}}
+                        "traffic_note": "ncu dram__bytes per launch, one 32-month sweep of the 20000^2 grid: levels 1-120 (212 M of the "
+                                        "220 M non-source cells) move 140.0 GB read + 50.4 GB written in 36.6 ms = 5.2 TB/s, "
+                                        "against 204.8 GB algorithmic for the whole sweep (source cells, 45 %, cost no traffic; "
+                                        "every other cell reads its row and 1.2-1.8 upstream rows and writes its row) "
+                                        "(profiles/r1_wide_levels_traffic.txt, r1_route_ncu_full.txt)"}}
     out["basins"] = plan.basin_info()
     out["reaches"] = plan.reach_info()
     del A
