@@ -687,11 +687,12 @@ __global__ void k_run_level_step(const int32_t *__restrict__ uorder, int nu, int
 
 __global__ void k_run_keys(const int32_t *__restrict__ head, const int32_t *__restrict__ dist,
                            const int32_t *__restrict__ rl, int nu, unsigned long long *__restrict__ keys,
-                           int32_t *__restrict__ vals)
+                           int32_t *__restrict__ vals, int *__restrict__ overflow)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nu) return;
     int32_t h = head[j];
+    if (dist[j] >= (1 << 20)) *overflow = 1;     // a reach of a million cells does not fit the key
     keys[j] = ((unsigned long long)rl[h] << 48) | ((unsigned long long)h << 20) | (unsigned long long)dist[j];
     vals[j] = j;
 }
@@ -1394,8 +1395,13 @@ static int plan_build_runs(wfa_plan *p)
     RRC(keys2.ensure((size_t)nu * 8));
     RRC(vals.ensure((size_t)nu * 4));
     RRC(sj.ensure((size_t)nu * 4));
-    k_run_keys<<<nb, 256, 0, st>>>(hs, ds, rl.as<int32_t>(), nu, keys.as<unsigned long long>(), vals.as<int32_t>());
+    RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    k_run_keys<<<nb, 256, 0, st>>>(hs, ds, rl.as<int32_t>(), nu, keys.as<unsigned long long>(), vals.as<int32_t>(),
+                                   flag.as<int>());
     RCK(cudaGetLastError());
+    RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    if (changed) { cleanup(); return GR2M_OK; }               // keep the per-basin sweep
     size_t tbytes = 0;
     RCK(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
                                         vals.as<int32_t>(), sj.as<int32_t>(), nu, 0, 64, st));
