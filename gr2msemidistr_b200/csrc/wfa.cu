@@ -773,20 +773,39 @@ __global__ void k_run_rowcell(const int32_t *__restrict__ row_off, const int32_t
     for (int r = b; r < e; ++r) rowcell[r] = r == e - 1 ? rcell[i] : -1;
 }
 
-// per reach: first/last stream row, head cell and the head's inflow list, in one 48-byte record
+__global__ void k_run_inv(const int32_t *__restrict__ sj, int nu, int32_t *__restrict__ inv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nu) inv[sj[i]] = i;
+}
+
+// per reach, one 80-byte record: first/last stream row, head cell, number of head inflows; the inflow
+// cells; and for every inflow the reach whose last cell it is (-1: below the cut, final before the sweep)
+constexpr int RINFO_VEC = 5;
 __global__ void k_run_pack(const int32_t *__restrict__ run_start, int nr, const int32_t *__restrict__ rcell,
                            const int32_t *__restrict__ rup_off, const uint32_t *__restrict__ rup_idx,
-                           const int32_t *__restrict__ row_off, int4 *__restrict__ rinfo)
+                           const int32_t *__restrict__ row_off, const int32_t *__restrict__ level, int cut,
+                           const int32_t *__restrict__ upos, const int32_t *__restrict__ inv,
+                           const int32_t *__restrict__ rank, int4 *__restrict__ rinfo)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nr) return;
     const int i0 = run_start[r], i1 = run_start[r + 1];
     const int o = rup_off[i0], n = rup_off[i0 + 1] - o;
-    uint32_t u[8];
-    for (int q = 0; q < 8; ++q) u[q] = q < n ? (rup_idx[o + q] & UP_ID) : 0u;
-    rinfo[3 * r + 0] = make_int4(row_off[i0], row_off[i1], rcell[i0], n);
-    rinfo[3 * r + 1] = make_int4((int)u[0], (int)u[1], (int)u[2], (int)u[3]);
-    rinfo[3 * r + 2] = make_int4((int)u[4], (int)u[5], (int)u[6], (int)u[7]);
+    int u[8], d[8];
+    for (int q = 0; q < 8; ++q) {
+        u[q] = 0; d[q] = -1;
+        if (q < n) {
+            u[q] = (int)(rup_idx[o + q] & UP_ID);
+            if (level[u[q]] >= cut) d[q] = rank[inv[upos[u[q]]]] - 1;     // rank = inclusive scan of reach starts
+        }
+    }
+    int4 *out = rinfo + (size_t)RINFO_VEC * r;
+    out[0] = make_int4(row_off[i0], row_off[i1], rcell[i0], n);
+    out[1] = make_int4(u[0], u[1], u[2], u[3]);
+    out[2] = make_int4(u[4], u[5], u[6], u[7]);
+    out[3] = make_int4(d[0], d[1], d[2], d[3]);
+    out[4] = make_int4(d[4], d[5], d[6], d[7]);
 }
 
 // Phase 1 of the reach sweep, fully parallel: everything a non-head cell adds besides its predecessor is
@@ -806,10 +825,10 @@ __global__ void __launch_bounds__(256) k_reach_gather(const int32_t *__restrict_
                                                       const T *__restrict__ A, T *__restrict__ S, int ld, int lds,
                                                       int nmonth)
 {
-    const long long ib = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G * G;
     const int g = threadIdx.x % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
-    if (ib >= nu) return;
+    for (long long ib = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G * G; ib < nu;
+         ib += (long long)gridDim.x * blockDim.x) {
     int m_rb = 0, m_nr = 0, m_c = 0, m_o = 0, m_n = 0;
     uint32_t m_e0 = UP_PRED, m_e1 = UP_PRED, m_e2 = UP_PRED;
     if (ib + g < nu) {
@@ -856,6 +875,7 @@ __global__ void __launch_bounds__(256) k_reach_gather(const int32_t *__restrict_
             __stcs(S + (size_t)rb * lds + j, acc);
         }
     }
+    }
 }
 
 // Phase 2: one warp per reach, months on the lanes, the reaches of one reach level per launch.  The head
@@ -869,30 +889,46 @@ template <typename T>
 __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__restrict__ rinfo,
                                                               const int32_t *__restrict__ rowcell, int r0, int r1,
                                                               const T *__restrict__ S, int lds, T *A, int ld,
-                                                              int nmonth)
+                                                              int nmonth, int *ticket, unsigned *done, unsigned epoch)
 {
     __shared__ alignas(128) T sbuf[RS_WARPS][RS_STAGES][RS_ROWS * 32];
     __shared__ alignas(16) int32_t scell[RS_WARPS][RS_STAGES][RS_ROWS];
     __shared__ alignas(8) uint64_t full[RS_WARPS][RS_STAGES];
     const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int run = r0 + blockIdx.x * RS_WARPS + w;
+    // dataflow mode (ticket != NULL): all reach levels in one launch.  Reaches are sorted by level, so every
+    // reach a head waits for has a smaller index; taking the index from a ticket makes "smaller index"
+    // mean "already running", whatever order the CTAs were dispatched in.
+    int run = blockIdx.x * RS_WARPS + w;
+    if (ticket) {
+        if (lane == 0) run = atomicAdd(ticket, 1);
+        run = __shfl_sync(0xffffffffu, run, 0);
+    }
+    run += r0;
     if (run >= r1) return;                        // warps never meet at a block barrier
     if (lane == 0) {
         for (int i = 0; i < RS_STAGES; ++i) mbar_init(&full[w][i], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    const int4 h0 = __ldg(rinfo + 3 * (size_t)run), h1 = __ldg(rinfo + 3 * (size_t)run + 1),
-               h2 = __ldg(rinfo + 3 * (size_t)run + 2);
+    const int4 *ri = rinfo + (size_t)RINFO_VEC * run;
+    const int4 h0 = __ldg(ri), h1 = __ldg(ri + 1), h2 = __ldg(ri + 2);
     const int rbeg = h0.x, rend = h0.y, c0 = h0.z, n0 = h0.w;
     const int up[8] = {h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w};
+    int mydep = -1;                               // lane q < 8 watches the reach that ends in inflow q
+    if (ticket) {
+        const int4 d0 = __ldg(ri + 3), d1 = __ldg(ri + 4);
+        const int dep[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (lane == q) mydep = dep[q];
+    }
     const int b0 = rbeg / RS_ROWS, nblk = rend > rbeg ? (rend + RS_ROWS - 1) / RS_ROWS - b0 : 0;
     // rows narrower than 32 values are contiguous in the stream: one copy per stage, row pitch lds in
     // shared memory too; wider rows are swept 32 months at a time, one copy per row
     const bool dense = lds <= 32;
     const int spitch = dense ? lds : 32;
     const size_t apitch = (size_t)ld * sizeof(T);
-    int done = 0;                                 // stream blocks consumed so far over all passes (ring position)
+    int done_blk = 0;                             // stream blocks consumed so far over all passes (ring position)
     for (int j0 = 0; j0 < nmonth; j0 += 32) {
         const int j = j0 + lane;
         const bool live = j < nmonth;
@@ -912,9 +948,18 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
         };
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int k = 0; k < min(nblk, RS_STAGES); ++k) issue(k, done + k);
+            for (int k = 0; k < min(nblk, RS_STAGES); ++k) issue(k, done_blk + k);
         }
         // reach head
+        if (ticket && j0 == 0) {
+            if (mydep >= 0) {
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + mydep) : "memory");
+                } while (seen != epoch);
+            }
+            __syncwarp();
+        }
         T acc = 0;
         if (live) {
             T v[8];
@@ -927,7 +972,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
             A[(size_t)c0 * ld + j] = acc;
         }
         for (int k = 0; k < nblk; ++k) {
-            const int pos = done + k, st = pos % RS_STAGES;
+            const int pos = done_blk + k, st = pos % RS_STAGES;
             mbar_wait(&full[w][st], (pos / RS_STAGES) & 1);
             const int base = (b0 + k) * RS_ROWS;
             const int lo = max(rbeg - base, 0), hi = min(rend - base, RS_ROWS);
@@ -954,7 +999,14 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_reach_sweep(const int4 *__res
                 issue(k + RS_STAGES, pos + RS_STAGES);
             }
         }
-        done += nblk;
+        done_blk += nblk;
+    }
+    if (ticket) {                                 // publish: the last cell of this reach is in A
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done + run), "r"(epoch) : "memory");
+        }
     }
 }
 
@@ -1105,7 +1157,7 @@ static void plan_free(wfa_plan *p)
     DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
                       &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx, &p->rcell, &p->rup_off,
-                      &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo};
+                      &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo, &p->rdone};
     for (DevBuf *d : bufs) d->release();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1451,10 +1503,15 @@ static int plan_build_runs(wfa_plan *p)
     RRC(p->rowcell.ensure(((size_t)nrows + 2 * RS_ROWS) * 4));        // the sweep copies whole RS_ROWS blocks
     RCK(cudaMemsetAsync(p->rowcell.p, 0xff, ((size_t)nrows + 2 * RS_ROWS) * 4, st));
     k_run_rowcell<<<nb, 256, 0, st>>>(p->row_off.as<int32_t>(), p->rcell.as<int32_t>(), nu, p->rowcell.as<int32_t>());
-    RRC(p->rinfo.ensure((size_t)nr * 48));
+    RRC(p->rinfo.ensure((size_t)nr * RINFO_VEC * 16));
+    RRC(p->rdone.ensure((size_t)nr * 4));
+    RCK(cudaMemsetAsync(p->rdone.p, 0, (size_t)nr * 4, st));
+    int32_t *inv = vals.as<int32_t>();            // the sort's input values are no longer needed
+    k_run_inv<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, inv);
     k_run_pack<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, p->rcell.as<int32_t>(),
                                                  p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(),
-                                                 p->row_off.as<int32_t>(), p->rinfo.as<int4>());
+                                                 p->row_off.as<int32_t>(), p->level.as<int32_t>(), lc,
+                                                 upos.as<int32_t>(), inv, rank.as<int32_t>(), p->rinfo.as<int4>());
     p->nrows = nrows;
     k_run_levels<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, sj.as<int32_t>(), rl.as<int32_t>(),
                                                    runrl.as<int32_t>());
@@ -1638,6 +1695,15 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
         l0 = p->nlevels;
         while (l0 > 1 && off[l0] - off[l0 - 1] <= width) --l0;
     }
+    // reach sweep: the stream buffer
+    const int nu = by_reach ? p->norder - off[p->comp_level] : 0;
+    const int lds = (nmonth + 3) & ~3;            // stream rows are multiples of 16 bytes for the bulk copies
+    T *S = nullptr;
+    if (by_reach && l0 < p->nlevels) {
+        int rc_ = p->rstream.ensure(((size_t)p->nrows + 2 * RS_ROWS) * lds * sizeof(T));
+        if (rc_) return rc_;
+        S = p->rstream.as<T>();
+    }
     // level 0 has no upstream cells: nothing to add
     {
         cudaLaunchAttribute attr[1];
@@ -1658,20 +1724,21 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     CK(cudaEventRecord(p->evm, st));
     if (l0 < p->nlevels) {
         if (by_reach) {
-            const int nu = p->norder - off[p->comp_level];
-            const int lds = (nmonth + 3) & ~3;    // stream rows are multiples of 16 bytes for the bulk copies
-            {
-                int rc_ = p->rstream.ensure(((size_t)p->nrows + 2 * RS_ROWS) * lds * sizeof(T));
-                if (rc_) return rc_;
-            }
-            T *S = p->rstream.as<T>();
             k_reach_gather<T, G><<<ceil_div(nu, gpb), 256, 0, st>>>(p->rcell.as<int32_t>(), p->rup_off.as<int32_t>(),
                                                                     p->rup_idx.as<uint32_t>(), p->row_off.as<int32_t>(), nu,
                                                                     A, S, ld, lds, nmonth);
-            for (size_t l = 0; l + 1 < p->h_rlv_off.size(); ++l) {
-                const int r0 = p->h_rlv_off[l], r1 = p->h_rlv_off[l + 1];
-                k_reach_sweep<T><<<ceil_div(r1 - r0, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
-                    p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), r0, r1, S, lds, A, ld, nmonth);
+            if (flags & WFA_NO_OVERLAP) {         // one launch per reach level
+                for (size_t l = 0; l + 1 < p->h_rlv_off.size(); ++l) {
+                    const int r0 = p->h_rlv_off[l], r1 = p->h_rlv_off[l + 1];
+                    k_reach_sweep<T><<<ceil_div(r1 - r0, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
+                        p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), r0, r1, S, lds, A, ld, nmonth, nullptr, nullptr, 0u);
+                }
+            } else {                              // all levels in one launch, heads wait for the reaches that feed them
+                p->epoch += 1;
+                CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
+                k_reach_sweep<T><<<ceil_div(p->nruns, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
+                    p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), 0, p->nruns, S, lds, A, ld, nmonth, p->ticket.as<int>(),
+                    p->rdone.as<unsigned>(), p->epoch);
             }
         } else if (by_basin) {
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));

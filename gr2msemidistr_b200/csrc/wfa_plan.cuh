@@ -23,7 +23,7 @@ struct wfa_plan {
     bool run_ok = false;
     int run_critical = 0;
     int nruns = 0;
-    DevBuf rcell, rup_off, rup_idx, run_start, row_off, rowcell, rstream, rinfo;
+    DevBuf rcell, rup_off, rup_idx, run_start, row_off, rowcell, rstream, rinfo, rdone;
     int nrows = 0;
     std::vector<int32_t> h_rlv_off;      // first reach of every reach level
 };
