@@ -741,6 +741,71 @@ __global__ void __launch_bounds__(256) k_fp64_peak_rrr(int iters, double seed, d
     if (r == 123.456) sink[0] = r;
 }
 
+// operand-mix variants of the same chains (development probe, not in the header):
+//   mode 0: fma(a, m, const)   two register operands + constant bank
+//   mode 1: a + m              DADD, two register operands
+//   mode 2: a * m              DMUL, two register operands
+//   mode 3: fma(a, a, c)       two distinct register pairs, one repeated
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp64_peak_mix(int iters, double seed, double *sink)
+{
+    double a[8], m[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        a[u] = seed + threadIdx.x + u;
+        m[u] = sink[1 + threadIdx.x * 16 + u];
+        c[u] = sink[1 + threadIdx.x * 16 + 8 + u];
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (MODE == 0) a[u] = __fma_rn(a[u], m[u], 1e-9);
+                if (MODE == 1) a[u] = __dadd_rn(a[u], m[u]);
+                if (MODE == 2) a[u] = __dmul_rn(a[u], m[u]);
+                if (MODE == 3) a[u] = __fma_rn(a[u], a[u], c[u]);
+            }
+        }
+    }
+    double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    if (r == 123.456) sink[0] = r;
+}
+
+extern "C" int gr2m_fp64_peak_mix(int mode, int iters, double *tinstr)
+{
+    REQUIRE(iters > 0 && tinstr && mode >= 0 && mode <= 3, "bad arguments");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    const int blocks = prop.multiProcessorCount * 8;
+    double *sink = nullptr;
+    CK(cudaMalloc(&sink, (1 + 256 * 16) * sizeof(double)));
+    CK(cudaMemset(sink, 0, (1 + 256 * 16) * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        if (mode == 0) k_fp64_peak_mix<0><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 1) k_fp64_peak_mix<1><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 2) k_fp64_peak_mix<2><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 3) k_fp64_peak_mix<3><<<blocks, 256>>>(iters, 1.0, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tinstr = 64.0 * (double)iters * 256.0 * blocks / (best * 1e-3) / 1e12;    // 1e12 thread-instructions/s
+    return GR2M_OK;
+}
+
 extern "C" int gr2m_fp64_peak_rrr(int iters, double *tflops)
 {
     REQUIRE(iters > 0 && tflops, "bad arguments");
