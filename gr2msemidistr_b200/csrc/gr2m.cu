@@ -287,17 +287,44 @@ __global__ void __launch_bounds__(128) k_gr2m_sim(SimArgs a)
     CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0, a.forcing_ok);
     double S = (a.S0 && ok) ? a.S0[cell] : 0.3 * p.X1;
     double R = (a.R0 && ok) ? a.R0[cell] : 0.5 * p.X2;
-    const double *f = a.F + (size_t)tile * a.ntime_pad * 64 + lane;
+    const double *__restrict__ f = a.F + (size_t)tile * a.ntime_pad * 64 + lane;
+    const double *__restrict__ den = a.den;
+    double *__restrict__ out = a.out;
     const size_t plane = (size_t)a.ntime * a.ncell_pad;
-    for (int t = 0; t < a.ntime; ++t) {
-        double Pr = f[(size_t)t * 64], Er = f[(size_t)t * 64 + 32];
-        StepOut o = FAST ? step_fast(p, Pr, Er, S, R, a.f32exp, tab) : step_literal(p, Pr, Er, S, R, a.f32exp);
-        size_t k = (size_t)t * a.ncell_pad + cell;
-        a.out[k] = o.Pc;
-        a.out[plane + k] = o.AE;
-        a.out[2 * plane + k] = S;
-        a.out[3 * plane + k] = o.Q;
-        a.out[4 * plane + k] = (p.area * o.Q) / a.den[t];
+    // the recursion is one dependent chain per thread: keep the forcing of the next U months in flight so a
+    // month costs its arithmetic, not a memory round trip (ntime_pad rows exist in F; den is guarded)
+    constexpr int U = 4;
+    double Pn[U], En[U], Dn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        Pn[u] = __ldg(f + (size_t)u * 64); En[u] = __ldg(f + (size_t)u * 64 + 32);
+        Dn[u] = u < a.ntime ? __ldg(den + u) : 1.0;
+    }
+    for (int t0 = 0; t0 < a.ntime; t0 += U) {
+        double Pc_[U], Ec_[U], Dc_[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { Pc_[u] = Pn[u]; Ec_[u] = En[u]; Dc_[u] = Dn[u]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tn = t0 + U + u;
+            if (tn < a.ntime) {
+                Pn[u] = __ldg(f + (size_t)tn * 64); En[u] = __ldg(f + (size_t)tn * 64 + 32); Dn[u] = __ldg(den + tn);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u;
+            if (t < a.ntime) {
+                StepOut o = FAST ? step_fast(p, Pc_[u], Ec_[u], S, R, a.f32exp, tab)
+                                 : step_literal(p, Pc_[u], Ec_[u], S, R, a.f32exp);
+                const size_t k = (size_t)t * a.ncell_pad + cell;
+                __stcs(out + k, o.Pc);
+                __stcs(out + plane + k, o.AE);
+                __stcs(out + 2 * plane + k, S);
+                __stcs(out + 3 * plane + k, o.Q);
+                __stcs(out + 4 * plane + k, (p.area * o.Q) / Dc_[u]);
+            }
+        }
     }
     if (ok) {
         if (a.S_end) a.S_end[cell] = S;
