@@ -115,3 +115,32 @@ def test_router_large_grid_many_sources(capi):
         dense = p.route(QS, src, off, cells, capi.WFA_ROUTE_DENSE)
     assert info["nnodes"] >= nsub * 0.9 and info["nactive"] > info["nnodes"]
     assert same(got, dense)
+
+
+def test_router_degenerate_geometries(capi, oracle):
+    rng = np.random.default_rng(11)
+    d8 = synth.d8_grid(60, 80, seed=4).numpy()
+    nod = np.flatnonzero(~((d8.ravel() >= 1) & (d8.ravel() <= 8)))
+    val = np.flatnonzero((d8.ravel() >= 1) & (d8.ravel() <= 8))
+    assert nod.size >= 3
+    QS = rng.uniform(1, 9, (3, 5))
+    with capi.Plan(d8) as p:
+        # every source on a nodata cell: nothing is routed, polygons see zeros (or nothing at all)
+        src = nod[:3].astype(np.int32)
+        off = np.array([0, 4, 4, 6], np.int32)
+        cells = np.concatenate([val[:4], nod[:2]]).astype(np.int32)
+        with p.router(src, off, cells) as r:
+            assert r.info()["nnodes"] == 0 and r.info()["nactive"] == 0
+            got = r.apply(QS)
+        assert same(got, p.route(QS, src, off, cells, capi.WFA_ROUTE_DENSE))
+        assert same(got, oracle.route(d8, QS, src, off, cells))
+        # no polygon has an interior cell: all maxima are -Inf, as R's max(numeric(0)) with a warning
+        src = val[[5, 50, 500]].astype(np.int32)
+        got = p.route(QS, src, np.zeros(4, np.int32), np.zeros(0, np.int32))
+        assert np.all(np.isneginf(got))
+        # one column, and more columns than one chunk of the dense path would take
+        off = np.array([0, 30, 60, 90], np.int32)
+        cells = rng.choice(val, 90).astype(np.int32)
+        for ncols in (1, 200):
+            Q = rng.uniform(0, 50, (3, ncols))
+            assert same(p.route(Q, src, off, cells), oracle.route(d8, Q, src, off, cells))
