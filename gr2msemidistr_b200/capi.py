@@ -23,7 +23,7 @@ OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_set_device", "gr2m_fp64_peak",
+    "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_release_cached_memory", "gr2m_set_device", "gr2m_fp64_peak",
     "gr2m_basin_create", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
@@ -81,6 +81,11 @@ def _i32(a):
 
 def device_count() -> int:
     return lib().gr2m_device_count()
+
+
+def release_cached_memory():
+    """Give the device blocks kept for the next handle back to the driver."""
+    _check(lib().gr2m_release_cached_memory())
 
 
 def set_device(device: int):

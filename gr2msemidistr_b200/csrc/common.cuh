@@ -33,6 +33,12 @@ int gr2m_current_device(void);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Device memory goes through a small per-process cache of freed blocks (gr2m.cu): handles are created and
+// destroyed around every call in the reference's workflow (one Run_/Optim_/Routing_ call = one handle), and
+// cudaFree of a few hundred MB costs milliseconds to tenths of a second.  `got` = the block's real size.
+int gr2m_dev_alloc(void **p, size_t bytes, size_t *got);
+void gr2m_dev_free(void *p, size_t bytes);
+
 // grow-only device buffer owned by a handle (capacity kept across calls)
 struct DevBuf {
     void *p = nullptr;
@@ -40,15 +46,13 @@ struct DevBuf {
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return GR2M_OK;
-        if (p) cudaFree(p);
+        if (p) gr2m_dev_free(p, cap);
         p = nullptr; cap = 0;
-        CK(cudaMalloc(&p, bytes));
-        cap = bytes;
-        return GR2M_OK;
+        return gr2m_dev_alloc(&p, bytes, &cap);
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) gr2m_dev_free(p, cap);
         p = nullptr; cap = 0;
     }
     template <typename T> T *as() { return static_cast<T *>(p); }

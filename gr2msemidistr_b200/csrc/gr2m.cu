@@ -14,7 +14,9 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <mutex>
 #include <new>
+#include <vector>
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing / device selection
@@ -41,6 +43,106 @@ extern "C" int gr2m_device_count(void)
         return 0;
     }
     return n;
+}
+
+// ---- cache of freed device blocks ------------------------------------------------------------------
+namespace {
+struct CachedBlock { void *p; size_t bytes; int dev; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+size_t g_cache_bytes = 0;
+constexpr size_t CACHE_MIN_BLOCK = 1ull << 20;      // smaller blocks are cheap to cudaMalloc/cudaFree
+constexpr size_t CACHE_MAX_BLOCK = 4ull << 30;      // the dense routing buffers are never kept
+constexpr size_t CACHE_MAX_TOTAL = 8ull << 30;
+bool cache_enabled()
+{
+    static const bool on = getenv("GR2M_NO_CACHE") == nullptr;
+    return on;
+}
+void cache_trim_locked(int dev)     // dev < 0: every device
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < g_cache.size();) {
+        if (dev < 0 || g_cache[i].dev == dev) {
+            cudaSetDevice(g_cache[i].dev);
+            cudaFree(g_cache[i].p);
+            g_cache_bytes -= g_cache[i].bytes;
+            g_cache[i] = g_cache.back();
+            g_cache.pop_back();
+        } else {
+            ++i;
+        }
+    }
+    cudaSetDevice(cur);
+}
+}  // namespace
+
+int gr2m_dev_alloc(void **p, size_t bytes, size_t *got)
+{
+    *p = nullptr; *got = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes >= CACHE_MIN_BLOCK && cache_enabled()) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); ++i) {
+            const CachedBlock &b = g_cache[i];
+            if (b.dev == dev && b.bytes >= bytes && b.bytes - bytes <= bytes / 4 &&
+                (best < 0 || b.bytes < g_cache[best].bytes))
+                best = (int)i;
+        }
+        if (best >= 0) {
+            *p = g_cache[best].p; *got = g_cache[best].bytes;
+            g_cache_bytes -= g_cache[best].bytes;
+            g_cache[best] = g_cache.back();
+            g_cache.pop_back();
+            return GR2M_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {           // give the cached blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            cache_trim_locked(dev);
+        }
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        gr2m_set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA;
+    }
+    *got = bytes;
+    return GR2M_OK;
+}
+
+void gr2m_dev_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes >= CACHE_MIN_BLOCK && bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
+        // like cudaFree, nothing may still be using the block when it changes hands
+        if (cudaDeviceSynchronize() == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            if (g_cache_bytes + bytes <= CACHE_MAX_TOTAL && g_cache.size() < 64) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                g_cache.push_back({p, bytes, dev});
+                g_cache_bytes += bytes;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
+
+extern "C" int gr2m_release_cached_memory(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_trim_locked(-1);
+    return GR2M_OK;
 }
 
 int gr2m_check_device(void)
