@@ -293,6 +293,7 @@ def main():
 
     import __graft_entry__ as g
     from gr2msemidistr_b200 import capi, synth
+    from gr2msemidistr_b200 import dist as gdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -408,7 +409,15 @@ def main():
 
         def e2e_step():
             t0 = time.perf_counter()
-            b = capi.Basin(Pp.numpy(), Ep.numpy(), area, nd, region, 1)
+            if world > 1:
+                # the table is replicated: every rank uploads the rows of cells/world subbasins from pinned
+                # memory and the ranks all-gather them over NVLink (gr2msemidistr_b200.dist.replicate_forcing)
+                Pd, Ed = gdist.replicate_forcing(Pp, Ep, dev)
+                b = capi.Basin(None, None, area, nd, region, 1, dev_ptrs=(Pd.data_ptr(), Ed.data_ptr()),
+                               shape=(a.cells, a.months), stream=torch.cuda.current_stream().cuda_stream)
+                del Pd, Ed
+            else:
+                b = capi.Basin(Pp.numpy(), Ep.numpy(), area, nd, region, 1)
             t1 = time.perf_counter()
             r = b.objective_batch(parp.numpy(), qobs, 36, capi.OF_KGE, flags, want_crit=False)
             t2 = time.perf_counter()
@@ -434,10 +443,13 @@ def main():
         dt = float(tt.item())
         same = bool(np.array_equal(of_e2e, of_host[s0:s1], equal_nan=True))
         e2e = {"value": units_step * n_e2e / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(P.nbytes + E.nbytes + area.nbytes + nd.nbytes + region.nbytes + par.nbytes + qobs.nbytes),
+               "h2d_bytes_per_step": int((P.nbytes + E.nbytes) // world + area.nbytes + nd.nbytes + region.nbytes + par.nbytes
+                                         + qobs.nbytes),
+               "h2d_note": "per rank" + ("; forcing rows uploaded 1/%d per rank and all-gathered (NCCL)" % world if world > 1 else ""),
                "d2h_bytes_per_step": int(nloc * 8), "steps": n_e2e, "matches_resident_run": same,
                "seconds_per_step": {k_: v_ / n_e2e for k_, v_ in e2e_parts.items()},
-               "api": "gr2m_basin_create + gr2m_objective_batch + gr2m_basin_destroy (pinned host buffers)"}
+               "api": ("dist.replicate_forcing + gr2m_basin_create_dev" if world > 1 else "gr2m_basin_create")
+                      + " + gr2m_objective_batch + gr2m_basin_destroy (pinned host buffers)"}
     else:
         basin.close()
 

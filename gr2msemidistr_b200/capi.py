@@ -24,7 +24,7 @@ OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_release_cached_memory", "gr2m_set_device", "gr2m_fp64_peak",
-    "gr2m_basin_create", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
+    "gr2m_basin_create", "gr2m_basin_create_dev", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_router_create", "wfa_router_destroy",
@@ -102,18 +102,28 @@ def fp64_peak_tflops(iters: int = 4096) -> float:
 class Basin:
     """gr2m_basin handle: the run-period forcing table and subbasin attributes resident in HBM."""
 
-    def __init__(self, P, E, area, ndays, region_id, nreg: int):
-        P, E = _f64(P), _f64(E)
-        if P.ndim != 2 or P.shape != E.shape:
-            raise ValueError("P and E must be [ncell, ntime] arrays of the same shape")
-        self.ncell, self.ntime = P.shape
+    def __init__(self, P, E, area, ndays, region_id, nreg: int, dev_ptrs=None, shape=None, stream: int = 0):
+        """P, E: [ncell, ntime] host arrays -- or, with dev_ptrs=(P_ptr, E_ptr) and shape=(ncell, ntime), the
+        same tables already in device memory, written on cudaStream_t `stream` (0 = complete)."""
+        if dev_ptrs is None:
+            P, E = _f64(P), _f64(E)
+            if P.ndim != 2 or P.shape != E.shape:
+                raise ValueError("P and E must be [ncell, ntime] arrays of the same shape")
+            self.ncell, self.ntime = P.shape
+        else:
+            self.ncell, self.ntime = (int(x) for x in shape)
         self.nreg = int(nreg)
         area, ndays, region_id = _f64(area), _i32(ndays), _i32(region_id)
         if area.shape != (self.ncell,) or region_id.shape != (self.ncell,) or ndays.shape != (self.ntime,):
             raise ValueError("area/region_id must be [ncell], ndays [ntime]")
         self._h = C.c_void_p()
-        _check(lib().gr2m_basin_create(C.c_int(self.ntime), C.c_int(self.ncell), _dp(P), _dp(E), _dp(area),
-                                       _ip(ndays), _ip(region_id), C.c_int(self.nreg), C.byref(self._h)))
+        if dev_ptrs is None:
+            _check(lib().gr2m_basin_create(C.c_int(self.ntime), C.c_int(self.ncell), _dp(P), _dp(E), _dp(area),
+                                           _ip(ndays), _ip(region_id), C.c_int(self.nreg), C.byref(self._h)))
+        else:
+            _check(lib().gr2m_basin_create_dev(C.c_int(self.ntime), C.c_int(self.ncell), C.c_void_p(dev_ptrs[0]),
+                                               C.c_void_p(dev_ptrs[1]), _dp(area), _ip(ndays), _ip(region_id),
+                                               C.c_int(self.nreg), C.c_void_p(stream), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h and _lib is not None:

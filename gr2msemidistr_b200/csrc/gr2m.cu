@@ -566,8 +566,10 @@ static void basin_free(gr2m_basin *b)
     delete b;
 }
 
-extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const double *E, const double *area,
-                                 const int *ndays, const int *region_id, int nreg, gr2m_basin **out)
+// on_device: P and E are device pointers (same layout), written on `src_stream` (NULL = already complete)
+static int basin_create_common(int ntime, int ncell, const double *P, const double *E, const double *area,
+                               const int *ndays, const int *region_id, int nreg, bool on_device,
+                               cudaStream_t src_stream, gr2m_basin **out)
 {
     REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
@@ -598,15 +600,19 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
     BCK(b->den.ensure(ntime * sizeof(double)));
     BCK(b->conv.ensure(ntime * sizeof(double) + 16));   // + a device flag used while tiling
     DevBuf rawP, rawE;
-    int r1 = rawP.ensure(nraw), r2 = rawE.ensure(nraw);
+    if (on_device && src_stream) b->stream = src_stream;      // tile in order after the producer of P and E
+    int r1 = on_device ? 0 : rawP.ensure(nraw), r2 = on_device ? 0 : rawE.ensure(nraw);
     if (r1 || r2) { rawP.release(); rawE.release(); basin_free(b); return r1 ? r1 : r2; }
+    const double *Pd = on_device ? P : rawP.as<double>(), *Ed = on_device ? E : rawE.as<double>();
     double *den = (double *)malloc(2 * ntime * sizeof(double));
     if (!den) { rawP.release(); rawE.release(); basin_free(b); gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
     for (int t = 0; t < ntime; ++t) { den[t] = 86.4 * (double)ndays[t]; den[ntime + t] = 1.0 / den[t]; }
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    step(cudaMemcpyAsync(rawP.p, P, nraw, cudaMemcpyHostToDevice, b->stream));
-    step(cudaMemcpyAsync(rawE.p, E, nraw, cudaMemcpyHostToDevice, b->stream));
+    if (!on_device) {
+        step(cudaMemcpyAsync(rawP.p, P, nraw, cudaMemcpyHostToDevice, b->stream));
+        step(cudaMemcpyAsync(rawE.p, E, nraw, cudaMemcpyHostToDevice, b->stream));
+    }
     step(cudaMemcpyAsync(b->area.p, area, ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     step(cudaMemcpyAsync(b->region.p, region_id, ncell * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     step(cudaMemcpyAsync(b->den.p, den, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -615,8 +621,7 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
         dim3 grid(b->ntiles, ceil_div(b->ntime_pad, 32)), blk(32, 8);
         int *bad = reinterpret_cast<int *>(b->conv.as<char>() + (size_t)ntime * sizeof(double));
         step(cudaMemsetAsync(bad, 0, sizeof(int), b->stream));
-        k_tile_forcing<<<grid, blk, 0, b->stream>>>(rawP.as<double>(), rawE.as<double>(), ncell, ntime, b->ntime_pad,
-                                                   b->F.as<double>(), bad);
+        k_tile_forcing<<<grid, blk, 0, b->stream>>>(Pd, Ed, ncell, ntime, b->ntime_pad, b->F.as<double>(), bad);
         step(cudaGetLastError());
         int hbad = 1;
         step(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -624,6 +629,7 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
         b->forcing_ok = hbad ? 0 : 1;
     }
     step(cudaStreamSynchronize(b->stream));
+    b->stream = b->own_stream;
     free(den);
     rawP.release(); rawE.release();
     if (e != cudaSuccess) {
@@ -633,6 +639,20 @@ extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const do
     }
     *out = b;
     return GR2M_OK;
+}
+
+extern "C" int gr2m_basin_create(int ntime, int ncell, const double *P, const double *E, const double *area,
+                                 const int *ndays, const int *region_id, int nreg, gr2m_basin **out)
+{
+    return basin_create_common(ntime, ncell, P, E, area, ndays, region_id, nreg, false, nullptr, out);
+}
+
+extern "C" int gr2m_basin_create_dev(int ntime, int ncell, const double *P_dev, const double *E_dev, const double *area,
+                                     const int *ndays, const int *region_id, int nreg, void *cuda_stream,
+                                     gr2m_basin **out)
+{
+    return basin_create_common(ntime, ncell, P_dev, E_dev, area, ndays, region_id, nreg, true, (cudaStream_t)cuda_stream,
+                               out);
 }
 
 extern "C" int gr2m_basin_destroy(gr2m_basin *b)

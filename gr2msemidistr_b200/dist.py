@@ -2,7 +2,9 @@
 
 The hot path shards without any data-path collective: every rank holds the whole
 forcing table and evaluates a slice of the parameter sets; the only exchange is an all-gather of
-the objective values (8 bytes per set) -- NCCL on GPUs, gloo in the CPU tests.
+the objective values (8 bytes per set) -- NCCL on GPUs, gloo in the CPU tests.  Replicating the table
+itself is the one place an exchange pays: N ranks each pushing all of it through the host's PCIe
+complex is slower than each pushing 1/N and all-gathering over NVLink (replicate_forcing).
 """
 from __future__ import annotations
 
@@ -34,6 +36,31 @@ def make_allgather(device=None):
     return allgather
 
 
+def replicate_forcing(P, E, device=None):
+    """Whole [ncell, ntime] tables on every rank's device: each rank uploads the rows of ncell/world
+    subbasins (from pinned host memory if P, E are pinned torch tensors) and the ranks all-gather them.
+    Returns torch tensors (P_dev, E_dev); without a process group it is a plain upload."""
+    import torch
+    import torch.distributed as dist
+    P, E = torch.as_tensor(P), torch.as_tensor(E)
+    ncell, ntime = P.shape
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        dev = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        return P.to(dev, non_blocking=True), E.to(dev, non_blocking=True)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = device or ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    m = -(-ncell // world)                                # rows per rank; the last slice is padded
+    lo, hi = min(rank * m, ncell), min((rank + 1) * m, ncell)
+    out = []
+    for X in (P, E):
+        mine = torch.zeros((m, ntime), dtype=torch.float64, device=dev)
+        mine[:hi - lo].copy_(X[lo:hi], non_blocking=True)
+        full = torch.empty((m * world, ntime), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, mine)
+        out.append(full[:ncell])
+    return out[0], out[1]
+
+
 def shard_spec():
     """(rank, world, allgather) for api.Optim_GR2MSemiDistr(shard=...), or None when not distributed."""
     import torch.distributed as dist
@@ -42,4 +69,4 @@ def shard_spec():
     return dist.get_rank(), dist.get_world_size(), make_allgather()
 
 
-__all__ = ["shard_range", "split_counts", "make_allgather", "shard_spec"]
+__all__ = ["shard_range", "split_counts", "make_allgather", "shard_spec", "replicate_forcing"]

@@ -89,6 +89,10 @@ int  gr2m_fp64_peak(int iters, double *tflops, float *ms);
  */
 int gr2m_basin_create(int ntime, int ncell, const double *P, const double *E, const double *area,
                       const int *ndays, const int *region_id, int nreg, gr2m_basin **out);
+/* Same, with P and E already in device memory (same layout); `cuda_stream` is the cudaStream_t they were
+ * written on (NULL = complete).  Used when N ranks each upload 1/N of the table and all-gather it. */
+int gr2m_basin_create_dev(int ntime, int ncell, const double *P_dev, const double *E_dev, const double *area,
+                          const int *ndays, const int *region_id, int nreg, void *cuda_stream, gr2m_basin **out);
 int gr2m_basin_destroy(gr2m_basin *b);
 /* run all work of this handle on a caller-provided cudaStream_t (NULL = the handle's own stream) */
 int gr2m_basin_set_stream(gr2m_basin *b, void *cuda_stream);

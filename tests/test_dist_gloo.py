@@ -40,6 +40,9 @@ def _worker(rank, world, port, q):
 
         shard = gdist.shard_spec()
         assert shard is not None and shard[0] == rank and shard[1] == world
+        # every rank ends up with the whole table although each contributed only its rows (5 rows over 2 ranks: 3 + 2)
+        Pd, Ed = gdist.replicate_forcing(P, E)
+        assert np.array_equal(Pd.numpy(), P) and np.array_equal(Ed.numpy(), E)
         par = synth.param_sets(21)                               # 21 sets over 2 ranks: 10 + 11
         full = _evaluate(obj, par, shard)
         lo, hi = gdist.shard_range(21, rank, world)

@@ -108,3 +108,25 @@ def test_plain_c_caller_runs_on_the_gpu(capi, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "set 0: 1 - NSE = 0.000" in out.stdout and "set 1:" in out.stdout
+
+
+def test_basin_from_device_tables(capi):
+    # gr2m_basin_create_dev: the forcing tables already in HBM (what replicate_forcing hands over)
+    import torch
+    P, E, area, nd = synth.forcing(70, 36)
+    region = (np.arange(70) % 3).astype(np.int32)
+    par = synth.param_sets(9, nreg=3)
+    qobs = synth.qobs_from(np.full(36, 55.0))
+    with capi.Basin(P, E, area, nd, region, 3) as b:
+        want = b.objective_batch(par, qobs, 6, capi.OF_NSE)
+        sim = b.run(par[0])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        Pd, Ed = torch.from_numpy(P).cuda(non_blocking=True), torch.from_numpy(E).cuda(non_blocking=True)
+    with capi.Basin(None, None, area, nd, region, 3, dev_ptrs=(Pd.data_ptr(), Ed.data_ptr()), shape=P.shape,
+                    stream=st.cuda_stream) as b:
+        got = b.objective_batch(par, qobs, 6, capi.OF_NSE)
+        sim2 = b.run(par[0])
+    assert np.array_equal(got["of"], want["of"]) and np.array_equal(got["crit"], want["crit"], equal_nan=True)
+    for k in ("PR", "AE", "SM", "RU", "QS"):
+        assert np.array_equal(sim[k], sim2[k])
