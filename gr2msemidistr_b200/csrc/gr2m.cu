@@ -280,15 +280,19 @@ constexpr int TM2 = 8;
 constexpr int NST2 = 4;
 constexpr int STAGE2_DBL = TM2 * 64;
 
+// 2^(j/2048) table in shared memory (16 KiB) -> 67 KiB per CTA, 3 CTAs (24 warps) per SM; the kernel is bound
+// by instruction dispatch, not by occupancy (4 CTAs with the 256-entry table were no faster)
+constexpr int CALIB_TAB = 2048, CALIB_CTAS = 3;
+
 template <bool FAST>
-__global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
+__global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);   // NST2 * STAGE2_DBL
     double *qacc = stage + NST2 * STAGE2_DBL;               // SPB * ntime_pad
     double *tconv = qacc + SPB * a.ntime_pad;               // ntime_pad
-    double *tab = tconv + a.ntime_pad;                      // 256: 2^(j/256)
-    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 256);   // NST2
+    double *tab = tconv + a.ntime_pad;                      // CALIB_TAB: 2^(j/2048)
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + CALIB_TAB);   // NST2
     int *left = reinterpret_cast<int *>(full + NST2);          // NST2: warps that have left the stage
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(SPB * 32, 4) k_gr2m_calib2(CalibArgs a)
 
     for (int i = tid; i < SPB * a.ntime_pad; i += blockDim.x) qacc[i] = 0.0;
     for (int i = tid; i < a.ntime_pad; i += blockDim.x) tconv[i] = i < a.ntime ? a.tconv[i] : 1.0;
-    tab[tid] = c_exp2_tab256[tid];   // blockDim.x == 256
+    for (int i = tid; i < CALIB_TAB; i += blockDim.x) tab[i] = g_exp2_tab2048[i];
     if (tid < NST2) left[tid] = 0;
     if (tid == 0) {
         for (int i = 0; i < NST2; ++i) mbar_init(&full[i], 1);
@@ -532,6 +536,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 7: r = div_fast3(x[i], y[i]); break;
         case 8: r = exp_tab256(x[i], tab256); break;
         case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
+        case 10: r = exp_tab2048(x[i], g_exp2_tab2048); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;
@@ -790,7 +795,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
     a.forcing_ok = b->forcing_ok;
-    size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + 256) * sizeof(double) + NST2 * 12;
+    size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + CALIB_TAB) * sizeof(double) + NST2 * 12;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
     auto kern = fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,6 +32,11 @@ __constant__ double c_exp2_tab256[256] = {
 #include "exp2_tab256.inc"
 };
 
+// 2^(j/2048), j = 0..2047 (16 KiB, global memory; staged in shared memory by k_gr2m_calib2)
+__device__ const double g_exp2_tab2048[2048] = {
+#include "exp2_tab2048.inc"
+};
+
 #define GR2M_MAGIC 6755399441055744.0   /* 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51 */
 
 // 64-bit literals that do not fit an instruction immediate.  Kept in constant memory so DFMA/DMUL
@@ -39,7 +44,7 @@ __constant__ double c_exp2_tab256[256] = {
 // (the first build spent ~60 of its ~200 instructions per month on such moves).
 struct MathK {
     double magic, nmagic, tenth, inv_ln2_32, nln2_32_hi, ln2_32_lo, c6, c5, c4, c3, two_ninths, third, tie_thr,
-        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo;
+        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo, inv_ln2_2048, nln2_2048;
 };
 __constant__ MathK KC = {GR2M_MAGIC,
                          -GR2M_MAGIC,
@@ -57,7 +62,9 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          -9.9341074625651041667e-9,   // -((double)(1.f/3.f) - 1/3)
                          0x1.71547652b82fep+8,        // 256 / ln 2
                          -0x1.62e42fefa0000p-9,       // -(ln2/256) high part (38 significant bits)
-                         -0x1.cf79abc9e3b3ap-48};     // -(ln2/256) low part
+                         -0x1.cf79abc9e3b3ap-48,      // -(ln2/256) low part
+                         0x1.71547652b82fep+11,       // 2048 / ln 2
+                         -0x1.62e42fefa39efp-12};     // -(ln2/2048) rounded to nearest
 
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
@@ -159,6 +166,22 @@ __device__ __forceinline__ double exp_tab256(double x, const double *__restrict_
     p = __fma_rn(p, r, 1.0);
     double v = __dmul_rn(p, tab[ki & 255]);
     return __hiloint2double(__double2hiint(v) + ((ki >> 8) << 20), __double2loint(v));
+}
+
+// 2048-entry table: |r| <= ln2/4096 = 1.7e-4, degree-3 Taylor (remainder 3.4e-17) and a one-FMA argument
+// reduction (here 0 <= x <= 26, so |k| <= 76 800 and the rounding of ln2/2048 costs <= 1.4e-15 on r):
+// 7 FP64-pipe instructions.
+__device__ __forceinline__ double exp_tab2048(double x, const double *__restrict__ tab)
+{
+    double t = __fma_rn(x, KC.inv_ln2_2048, KC.magic);
+    int ki = __double2loint(t);
+    double kd = __dadd_rn(t, KC.nmagic);
+    double r = __fma_rn(kd, KC.nln2_2048, x);      // |kd| <= 76 800: the constant's rounding costs <= 1.4e-15 on r
+    double p = __fma_rn(r, KC.c3, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    double v = __dmul_rn(p, tab[ki & 2047]);
+    return __hiloint2double(__double2hiint(v) + ((ki >> 11) << 20), __double2loint(v));
 }
 
 __device__ __forceinline__ double rcp_seed(double d)
@@ -288,13 +311,12 @@ __device__ __forceinline__ double step_fast3(const CellPar &p, double Praw, doub
         np_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fp, Praw)), 10.0);
         ne_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fe, Eraw)), 10.0);
     }
-    double Pc = np_ * KC.tenth;
-    double a = exp_tab256(clamp26(np_ * p.c01), tab);
-    double b = exp_tab256(clamp26(ne_ * p.c01), tab);
+    double a = exp_tab2048(clamp26(np_ * p.c01), tab);
+    double b = exp_tab2048(clamp26(ne_ * p.c01), tab);
     double am = __fma_rn(a, 0.5, -0.5), ap = __fma_rn(a, 0.5, 0.5);
     double s = S * p.iX1;
     double S1 = div_fast3(__fma_rn(p.X1, am, S * ap), __fma_rn(s, am, ap));
-    double P1 = (Pc + S) - S1;
+    double P1 = __fma_rn(np_, KC.tenth, S) - S1;        // Pc + S - S1 with Pc = n/10 formed inside the FMA
     double bm = __fma_rn(b, 0.5, -0.5), bp = __fma_rn(b, 0.5, 0.5);
     double S2 = div_fast3(S1, __fma_rn(__fma_rn(S1, -p.iX1, 1.0), bm, bp));
     double sr = S2 * p.iX1;

@@ -44,6 +44,10 @@ def test_device_math_building_blocks(capi, oracle, rng):
     assert np.max(np.abs(capi.debug_math(6, n, dd) / (n / dd) - 1)) < 4.5e-16      # the one-Newton-step variant in use
     assert np.max(np.abs(capi.debug_math(7, n, dd) / (n / dd) - 1)) < 6e-16        # cubic-step variant (not in use unless it passes here)
     assert np.max(np.abs(capi.debug_math(8, e) / np.exp(e) - 1)) < 7e-16           # 256-entry table, degree 4
+    # 2048-entry table, degree 3, one-FMA reduction (shipped calibration step): <= 1.4e-15 at x = 26 by construction
+    assert np.max(np.abs(capi.debug_math(10, e) / np.exp(e) - 1)) < 2.5e-15
+    small = e[e < 3]
+    assert np.max(np.abs(capi.debug_math(10, small) / np.exp(small) - 1)) < 7e-16
     assert np.array_equal(capi.debug_math(9, x), want)                             # rint by the conversion unit
     c = rng.uniform(1, 2, 200000)
     assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 7e-16
