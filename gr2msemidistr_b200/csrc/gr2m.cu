@@ -229,6 +229,7 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.fp10 = p.fp * 10.0;
     p.fe10 = p.fe * 10.0;
     p.c01 = 0.1 * p.i2X1;
+    p.g = p.c01 * 0x1.71547652b82fep+11;     // * 2048/ln2: exp arguments in table-index units
     p.area = area;
     // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
     p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? 0.499 : -1.0;
@@ -330,7 +331,8 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
         const int cell = tile * 32 + lane;
         const bool cell_ok = cell < a.ncell;
         CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0, a.forcing_ok);
-        double S = 0.3 * p.X1, R = 0.5 * p.X2;
+        // FAST carries the production store as S/X1 (step_fast4); airGR's default start is 0.3 X1, 0.5 X2
+        double S = FAST ? 0.3 : 0.3 * p.X1, R = 0.5 * p.X2;
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
             const int st = g % NST2;
             mbar_wait(&full[st], (g / NST2) & 1);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
                 for (int m = 0; m < 8; ++m) {
                     double Pr = sp[m * 64], Er = sp[m * 64 + 32];
                     if (FAST) {
-                        v[m] = p.area * step_fast3(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
+                        v[m] = p.area * step_fast4(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
                     } else {
                         StepOut o = step_literal(p, Pr, Er, S, R, a.f32exp);
                         v[m] = (p.area * o.Q) / tc[m];
@@ -537,6 +539,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 8: r = exp_tab256(x[i], tab256); break;
         case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
         case 10: r = exp_tab2048(x[i], g_exp2_tab2048); break;
+        case 11: r = 2.0 * exp_idx2048_half(clamp_u26(x[i] * 0x1.71547652b82fep+11), g_exp2_tab2048); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;

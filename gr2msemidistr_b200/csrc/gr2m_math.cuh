@@ -6,8 +6,9 @@
 //   step_fast    : same algebra with the two tanh divisions folded into the store updates
 //                  (3 divisions instead of 12), a table-driven exp, a Halley-refined reciprocal cube
 //                  root and Newton-refined MUFU reciprocals; returns every series (simulation mode).
-//   step_fast3   : calibration mode (only Q leaves the thread): additionally a 256-entry exp table,
-//                  halved tanh terms, rint by the conversion unit, one division step less.
+//   step_fast4   : calibration mode (only Q leaves the thread): production store carried as S/X1, exp
+//                  arguments in units of a 2048-entry table's index, halved tanh terms straight from
+//                  the table, rint by the conversion unit, one division step less.
 // Every building block is accurate to 1-2 ulp, so they agree to ~1e-14 relative; tests hold all
 // of them to 1e-10 against the CPU oracle.
 // The forcing correction round(f*x, 1) (R/Run_GR2MSemiDistr.R:101-102) is BIT-EXACT in both: a wrong
@@ -44,7 +45,7 @@ __device__ const double g_exp2_tab2048[2048] = {
 // (the first build spent ~60 of its ~200 instructions per month on such moves).
 struct MathK {
     double magic, nmagic, tenth, inv_ln2_32, nln2_32_hi, ln2_32_lo, c6, c5, c4, c3, two_ninths, third, tie_thr,
-        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo, inv_ln2_2048, nln2_2048;
+        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo, inv_ln2_2048, nln2_2048, e1, e2, e3;
 };
 __constant__ MathK KC = {GR2M_MAGIC,
                          -GR2M_MAGIC,
@@ -64,7 +65,10 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          -0x1.62e42fefa0000p-9,       // -(ln2/256) high part (38 significant bits)
                          -0x1.cf79abc9e3b3ap-48,      // -(ln2/256) low part
                          0x1.71547652b82fep+11,       // 2048 / ln 2
-                         -0x1.62e42fefa39efp-12};     // -(ln2/2048) rounded to nearest
+                         -0x1.62e42fefa39efp-12,      // -(ln2/2048) rounded to nearest
+                         0x1.62e42fefa39efp-12,       // L = ln2/2048
+                         0x1.ebfbdff82c58fp-25,       // L^2/2
+                         0x1.c6b08d704a0c0p-38};      // L^3/6
 
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
@@ -247,7 +251,7 @@ __device__ __forceinline__ double rcbrt_fast(double c)
 // ---- the month step -----------------------------------------------------------------------------
 struct CellPar {
     double X1, X2, iX1, i2X1, fp, fe, area, thr;   // i2X1 = 2/X1; thr: see r_round1
-    double fp10, fe10, c01;                        // 10 fp, 10 fe, 0.1 * 2/X1 (calibration kernel only)
+    double fp10, fe10, c01, g;                     // 10 fp, 10 fe, 0.1 * 2/X1, c01 * 2048/ln2 (calibration kernel only)
 };
 
 struct StepOut {
@@ -296,12 +300,39 @@ __device__ __forceinline__ StepOut step_fast(const CellPar &p, double Praw, doub
     return o;
 }
 
-// Calibration-mode step with the forcing correction reduced to its decision: n = rint(10 f x) is the
-// integer R's round() settles on (ties and anything within 1e-3 of one still go through the exact
-// candidate comparison), and the corrected value n/10 is only ever consumed inside 1e-16-tolerant
-// arithmetic here (it is not an output in this mode), so it is formed as n * 0.1 and the exp argument
-// as n * (0.1 * 2/X1) -- same rounding decision, at most one ulp from RN(n/10).
-__device__ __forceinline__ double step_fast3(const CellPar &p, double Praw, double Eraw, double &S, double &R,
+// exp in table-index units: u = x * 2048/ln2 >= 0, returns exp(x)/2.  k = rint(u) by the magic add, f = u - k
+// exactly (|f| <= 1/2), exp(f L) = 1 + f L + (f L)^2/2 + (f L)^3/6 with L = ln2/2048 folded into the
+// coefficients (remainder 3.4e-17): 2 DADD-class + 1 exact DADD + 3 DFMA + 1 DMUL, no separate reduction FMA.
+__device__ __forceinline__ double exp_idx2048_half(double u, const double *__restrict__ tab)
+{
+    double t = __dadd_rn(u, KC.magic);
+    int ki = __double2loint(t);
+    double kd = __dadd_rn(t, KC.nmagic);
+    double f = __dsub_rn(u, kd);
+    double p = __fma_rn(f, KC.e3, KC.e2);
+    p = __fma_rn(p, f, KC.e1);
+    p = __fma_rn(p, f, 1.0);
+    double v = __dmul_rn(p, tab[ki & 2047]);
+    return __hiloint2double(__double2hiint(v) + (((ki >> 11) - 1) << 20), __double2loint(v));
+}
+
+// min(u, Uc) on the high word by the integer ALU (see clamp26).  Uc = 76820.6875 is the first double with a
+// zero low word at or above 26 * 2048/ln2 = 76820.6255: the clamped argument is 26 + 2.1e-5, which moves
+// tanh(13) = 1 - 1.0e-11 by 2e-16.
+__device__ __forceinline__ double clamp_u26(double u)
+{
+    return __double2hiint(u) >= 0x40F2C14B ? 76820.6875 : u;
+}
+
+// Calibration-mode step (shipped).  Two reductions of the per-month work:
+//  * the forcing correction is reduced to its decision: n = rint(10 f x) is the integer R's round() settles
+//    on (ties and anything within 1e-3 of one still go through the exact candidate comparison); the corrected
+//    value n/10 is only ever consumed inside 1e-16-tolerant arithmetic here (it is not an output in this
+//    mode), so it enters as n * 0.1 inside an FMA and the exp argument as n * g, g = 0.2/X1 * 2048/ln2;
+//  * the production store is carried as s = S/X1: s1 = (s ap + am)/(ap + s am), s2 = s1/(bp + (1 - s1) bm),
+//    s' = s2 (1 + s2^3)^(-1/3), with am = (a-1)/2, ap = (a+1)/2 (a = e^{2P/X1}; the table gives a/2 directly),
+//    and X1 re-enters once: R + P1 + P2 = R + Pc + X1 ((s - s1) + (s2 - s')).
+__device__ __forceinline__ double step_fast4(const CellPar &p, double Praw, double Eraw, double &s, double &R,
                                              bool f32exp, const double *__restrict__ tab)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
@@ -311,22 +342,21 @@ __device__ __forceinline__ double step_fast3(const CellPar &p, double Praw, doub
         np_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fp, Praw)), 10.0);
         ne_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fe, Eraw)), 10.0);
     }
-    double a = exp_tab2048(clamp26(np_ * p.c01), tab);
-    double b = exp_tab2048(clamp26(ne_ * p.c01), tab);
-    double am = __fma_rn(a, 0.5, -0.5), ap = __fma_rn(a, 0.5, 0.5);
-    double s = S * p.iX1;
-    double S1 = div_fast3(__fma_rn(p.X1, am, S * ap), __fma_rn(s, am, ap));
-    double P1 = __fma_rn(np_, KC.tenth, S) - S1;        // Pc + S - S1 with Pc = n/10 formed inside the FMA
-    double bm = __fma_rn(b, 0.5, -0.5), bp = __fma_rn(b, 0.5, 0.5);
-    double S2 = div_fast3(S1, __fma_rn(__fma_rn(S1, -p.iX1, 1.0), bm, bp));
-    double sr = S2 * p.iX1;
-    double c = __fma_rn(sr * sr, sr, 1.0);
+    double a2 = exp_idx2048_half(clamp_u26(np_ * p.g), tab);
+    double b2 = exp_idx2048_half(clamp_u26(ne_ * p.g), tab);
+    double am = a2 - 0.5, ap = a2 + 0.5;
+    double s1 = div_fast3(__fma_rn(s, ap, am), __fma_rn(s, am, ap));
+    double bm = b2 - 0.5, bp = b2 + 0.5;
+    double s2 = div_fast3(s1, __fma_rn(1.0 - s1, bm, bp));
+    double c = __fma_rn(s2 * s2, s2, 1.0);
     double y = rcbrt_fast(c);
     if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
-    S = S2 * y;
-    double R2 = p.X2 * (R + (P1 + (S2 - S)));
+    double sn = s2 * y;
+    double d = (s - s1) + (s2 - sn);
+    double R2 = p.X2 * __fma_rn(p.X1, d, __fma_rn(np_, KC.tenth, R));
     double Q = div_fast3(R2 * R2, R2 + 60.0);
     R = R2 - Q;
+    s = sn;
     return Q;
 }
 

@@ -48,6 +48,11 @@ def test_device_math_building_blocks(capi, oracle, rng):
     assert np.max(np.abs(capi.debug_math(10, e) / np.exp(e) - 1)) < 2.5e-15
     small = e[e < 3]
     assert np.max(np.abs(capi.debug_math(10, small) / np.exp(small) - 1)) < 7e-16
+    # the shipped form: argument in table-index units, exp(x)/2 (x * 2048/ln2 costs <= 2 ulp of x on the exponent)
+    assert np.max(np.abs(capi.debug_math(11, e) / np.exp(e) - 1)) < 8e-15
+    assert np.max(np.abs(capi.debug_math(11, small) / np.exp(small) - 1)) < 1.2e-15
+    big = np.array([26.0, 27.0, 1e3, 7.6e5])                  # clamped like min(WS, 13): exp(26) up to 2.2e-5
+    assert np.max(np.abs(capi.debug_math(11, big) / np.exp(26.0) - 1)) < 3e-5
     assert np.array_equal(capi.debug_math(9, x), want)                             # rint by the conversion unit
     c = rng.uniform(1, 2, 200000)
     assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 7e-16
