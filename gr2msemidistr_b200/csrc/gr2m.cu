@@ -232,7 +232,7 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.g = p.c01 * 0x1.71547652b82fep+11;     // * 2048/ln2: exp arguments in table-index units
     p.area = area;
     // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
-    p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? 0.499 : -1.0;
+    p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? GR2M_TIE_THR : -1.0;
     return p;
 }
 
@@ -529,7 +529,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
     if (i >= n) return;
     double r;
     switch (op) {
-        case 0: r = r_round1(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
+        case 0: r = r_round1(x[i], fabs(x[i]) < 1e14 ? GR2M_TIE_THR : -1.0); break;
         case 1: r = r_round1_exact(x[i]); break;
         case 2: r = exp_tab(x[i], tab); break;
         case 3: r = div_fast(x[i], y[i]); break;
@@ -537,7 +537,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 6: r = div_fast1(x[i], y[i]); break;
         case 7: r = div_fast3(x[i], y[i]); break;
         case 8: r = exp_tab256(x[i], tab256); break;
-        case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? 0.499 : -1.0); break;
+        case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? GR2M_TIE_THR : -1.0); break;
         case 10: r = exp_tab2048(x[i], g_exp2_tab2048); break;
         case 11: r = 2.0 * exp_idx2048_half(clamp_u26(x[i] * 0x1.71547652b82fep+11), g_exp2_tab2048); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;

@@ -38,6 +38,7 @@ __device__ const double g_exp2_tab2048[2048] = {
 #include "exp2_tab2048.inc"
 };
 
+#define GR2M_TIE_THR 0.49999            /* see r_round1 */
 #define GR2M_MAGIC 6755399441055744.0   /* 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51 */
 
 // 64-bit literals that do not fit an instruction immediate.  Kept in constant memory so DFMA/DMUL
@@ -59,7 +60,7 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          0x1.5555555555555p-3,    // 1/6
                          0x1.c71c71c71c71cp-3,    // 2/9
                          0x1.5555555555555p-2,    // 1/3
-                         0.499,
+                         GR2M_TIE_THR,
                          -9.9341074625651041667e-9,   // -((double)(1.f/3.f) - 1/3)
                          0x1.71547652b82fep+8,        // 256 / ln 2
                          -0x1.62e42fefa0000p-9,       // -(ln2/256) high part (38 significant bits)
@@ -94,16 +95,18 @@ __device__ __noinline__ double r_round1_exact(double x)
     return copysign(r, x);
 }
 
-// Same result, cheap common case: away from a decimal tie the winner is rint(10x)/10 (for either
-// sign).  Valid while |10x| < 2^51; `thr` is 0.499 when the caller has bounded |x| < 1e14 (forcing
-// checked at upload, factors at parameter load) and -1 otherwise, which sends every value down
-// the exact path.  NaN fails the comparison and takes the exact path too.
+// Same result, cheap common case: away from a decimal tie the winner is rint(10x)/10 (for either sign).
+// R's candidate comparison can only disagree with rint(10x) when 10x is within a few ulp(10x) of a tie, so
+// the cheap path is taken when |10x - rint(10x)| < GR2M_TIE_THR = 0.49999 and |10x| < 1e9 (ulp(1e9) = 1.2e-7,
+// 80 times inside the 1e-5 window); everything else -- ties, huge values, NaN -- takes the exact path.  `thr`
+// is GR2M_TIE_THR, or -1 to send every value down the exact path.  With the earlier 1e-3 window one warp in
+// eight (64 corrections per warp and month) left the fast path; now one in 800.
 __device__ __forceinline__ double r_round1(double x, double thr)
 {
     double x10 = __dmul_rn(x, 10.0);
     double n = __dadd_rn(__dadd_rn(x10, KC.magic), KC.nmagic);
     double f = __dsub_rn(x10, n);
-    if (!(fabs(f) < thr)) return r_round1_exact(x);
+    if (!(fabs(f) < thr) || !(fabs(x10) < 1e9)) return r_round1_exact(x);
     return div10_rn(n);
 }
 

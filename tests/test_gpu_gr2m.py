@@ -30,6 +30,12 @@ def test_device_math_building_blocks(capi, oracle, rng):
     # R round(x,1): fast path and exact path bit-identical to the oracle, incl. exact decimal ties
     x = np.concatenate([rng.uniform(0, 4000, 200000), 1.186 * (rng.integers(0, 40000, 200000) / 10.0),
                         rng.integers(0, 80000, 100000) / 20.0, [0.0, 0.05, 0.15, 0.25, 0.35, 29.65, 1e-9, 3839.95, -0.15, -7.25]])
+    # adversarial: 10x within 1e-12 ... 1e-3 of a decimal tie, at magnitudes up to where ulp(10x) nears the
+    # 1e-5 window of the cheap path (it must hand those to the exact path, not decide them)
+    k = np.concatenate([rng.integers(0, 400000, 20000), rng.integers(10**6, 10**9, 20000),
+                        rng.integers(10**9, 2**33, 5000)]).astype(np.float64)
+    delta = rng.choice([0.0, 1e-12, 1e-10, 1e-8, 1e-6, 5e-6, 9e-6, 1.1e-5, 2e-5, 1e-4, 1e-3], k.size) * rng.choice([-1, 1], k.size)
+    x = np.concatenate([x, (k + 0.5 + delta) / 10.0, -(k[:5000] + 0.5 + delta[:5000]) / 10.0])
     want = oracle.r_round(x, 1)
     assert np.array_equal(capi.debug_math(0, x), want)
     assert np.array_equal(capi.debug_math(1, x), want)
