@@ -230,6 +230,8 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.fe10 = p.fe * 10.0;
     p.c01 = 0.1 * p.i2X1;
     p.g = p.c01 * 0x1.71547652b82fep+11;     // * 2048/ln2: exp arguments in table-index units
+    p.cP = 0.1 * p.iX1;
+    p.kappa = 60.0 * p.iX1;
     p.area = area;
     // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
     p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? GR2M_TIE_THR : -1.0;
@@ -285,7 +287,7 @@ constexpr int STAGE2_DBL = TM2 * 64;
 // by instruction dispatch, not by occupancy (4 CTAs with the 256-entry table were no faster)
 constexpr int CALIB_TAB = 2048, CALIB_CTAS = 3;
 
-template <bool FAST>
+template <bool FAST, bool F32EXP>
 __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -331,8 +333,9 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
         const int cell = tile * 32 + lane;
         const bool cell_ok = cell < a.ncell;
         CellPar p = load_par(par, a.nreg, cell_ok ? a.region[cell] : 0, cell_ok ? a.area[cell] : 0.0, a.forcing_ok);
-        // FAST carries the production store as S/X1 (step_fast4); airGR's default start is 0.3 X1, 0.5 X2
-        double S = FAST ? 0.3 : 0.3 * p.X1, R = 0.5 * p.X2;
+        // FAST carries both stores divided by X1 (step_fast4); airGR's default start is 0.3 X1, 0.5 X2
+        double S = FAST ? 0.3 : 0.3 * p.X1, R = FAST ? 0.5 * p.X2 * p.iX1 : 0.5 * p.X2;
+        const double aX1 = p.area * p.X1;
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
             const int st = g % NST2;
             mbar_wait(&full[st], (g / NST2) & 1);
@@ -344,9 +347,9 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
                 for (int m = 0; m < 8; ++m) {
                     double Pr = sp[m * 64], Er = sp[m * 64 + 32];
                     if (FAST) {
-                        v[m] = p.area * step_fast4(p, Pr, Er, S, R, a.f32exp, tab);   // x conv[t] after the reduction
+                        v[m] = aX1 * step_fast4<F32EXP>(p, Pr, Er, S, R, tab);   // x conv[t] after the reduction
                     } else {
-                        StepOut o = step_literal(p, Pr, Er, S, R, a.f32exp);
+                        StepOut o = step_literal(p, Pr, Er, S, R, F32EXP);
                         v[m] = (p.area * o.Q) / tc[m];
                     }
                 }
@@ -800,7 +803,8 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.forcing_ok = b->forcing_ok;
     size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + CALIB_TAB) * sizeof(double) + NST2 * 12;
     REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
-    auto kern = fast ? k_gr2m_calib2<true> : k_gr2m_calib2<false>;
+    auto kern = fast ? (a.f32exp ? k_gr2m_calib2<true, true> : k_gr2m_calib2<true, false>)
+                     : (a.f32exp ? k_gr2m_calib2<false, true> : k_gr2m_calib2<false, false>);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, b->stream));
     kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);

@@ -254,7 +254,7 @@ __device__ __forceinline__ double rcbrt_fast(double c)
 // ---- the month step -----------------------------------------------------------------------------
 struct CellPar {
     double X1, X2, iX1, i2X1, fp, fe, area, thr;   // i2X1 = 2/X1; thr: see r_round1
-    double fp10, fe10, c01, g;                     // 10 fp, 10 fe, 0.1 * 2/X1, c01 * 2048/ln2 (calibration kernel only)
+    double fp10, fe10, c01, g, cP, kappa;          // 10 fp, 10 fe, 0.1 * 2/X1, c01 * 2048/ln2, 0.1/X1, 60/X1 (calibration kernel only)
 };
 
 struct StepOut {
@@ -334,9 +334,11 @@ __device__ __forceinline__ double clamp_u26(double u)
 //    mode), so it enters as n * 0.1 inside an FMA and the exp argument as n * g, g = 0.2/X1 * 2048/ln2;
 //  * the production store is carried as s = S/X1: s1 = (s ap + am)/(ap + s am), s2 = s1/(bp + (1 - s1) bm),
 //    s' = s2 (1 + s2^3)^(-1/3), with am = (a-1)/2, ap = (a+1)/2 (a = e^{2P/X1}; the table gives a/2 directly),
-//    and X1 re-enters once: R + P1 + P2 = R + Pc + X1 ((s - s1) + (s2 - s')).
-__device__ __forceinline__ double step_fast4(const CellPar &p, double Praw, double Eraw, double &s, double &R,
-                                             bool f32exp, const double *__restrict__ tab)
+//  * the routing store is carried as rho = R/X1 as well: rho2 = X2 (rho + Pc/X1 + (s - s1) + (s2 - s')),
+//    q = rho2^2/(rho2 + 60/X1) = Q/X1, rho' = rho2 - q; the caller scales q by area * X1 once per sum.
+template <bool F32EXP>
+__device__ __forceinline__ double step_fast4(const CellPar &p, double Praw, double Eraw, double &s, double &rho,
+                                             const double *__restrict__ tab)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
     double np_ = (double)__double2int_rn(xp10), ne_ = (double)__double2int_rn(xe10);
@@ -353,14 +355,14 @@ __device__ __forceinline__ double step_fast4(const CellPar &p, double Praw, doub
     double s2 = div_fast3(s1, __fma_rn(1.0 - s1, bm, bp));
     double c = __fma_rn(s2 * s2, s2, 1.0);
     double y = rcbrt_fast(c);
-    if (f32exp) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
+    if (F32EXP) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
     double sn = s2 * y;
     double d = (s - s1) + (s2 - sn);
-    double R2 = p.X2 * __fma_rn(p.X1, d, __fma_rn(np_, KC.tenth, R));
-    double Q = div_fast3(R2 * R2, R2 + 60.0);
-    R = R2 - Q;
+    double rho2 = p.X2 * (__fma_rn(np_, p.cP, rho) + d);
+    double q = div_fast3(rho2 * rho2, rho2 + p.kappa);
+    rho = rho2 - q;
     s = sn;
-    return Q;
+    return q;
 }
 
 __device__ __forceinline__ StepOut step_literal(const CellPar &p, double Praw, double Eraw, double &S,
