@@ -39,9 +39,23 @@ METRIC = "gr2m_cell_months_per_sec"
 UNIT = "cell-months/s"
 FLOP_PER_UNIT_ALGO = 67          # nominal FP64 operations per (cell, set, month)
 try:   # FP64-pipe instructions per unit of the shipped recursion kernel, counted by ncu (profiles/)
-    FP64_INSTR_PER_UNIT = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_instr.json")))["fp64_pipe_inst_per_unit"]
+    _cnt = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_instr.json")))
+    FP64_INSTR_PER_UNIT, ALL_INSTR_PER_UNIT = _cnt["fp64_pipe_inst_per_unit"], _cnt["all_thread_inst_per_unit"]
 except Exception:
-    FP64_INSTR_PER_UNIT = 91.7
+    FP64_INSTR_PER_UNIT, ALL_INSTR_PER_UNIT = 62.2, 116.6
+
+
+def dispatch_model(units, kernel_ms, clocks, sms=148):
+    """Dispatch cycles per warp and unit the instruction counts need (2 per FP64, 1 per other instruction)
+    against the cycles the kernel took per warp-unit and SM sub-partition."""
+    try:
+        mhz = float(clocks["sm_mhz"]) if clocks and clocks.get("sm_mhz") else 1965.0
+        need = 2.0 * FP64_INSTR_PER_UNIT + (ALL_INSTR_PER_UNIT - FP64_INSTR_PER_UNIT)
+        took = kernel_ms * 1e-3 * mhz * 1e6 * sms * 4 / (units / 32.0)
+        return {"cycles_needed_per_warp_unit": need, "cycles_taken_per_warp_unit": took, "frac": need / took,
+                "all_instr_per_unit": ALL_INSTR_PER_UNIT}
+    except Exception as ex:
+        return {"error": repr(ex)}
 
 
 def parse_args():
@@ -386,6 +400,9 @@ def main():
                 "frac_of_three_register_operand_peak": ach_tf / peak_rrr,
                 "kernel_ms": kernel_ms, "units_per_launch": units_kernel,
                 "fp64_instr_per_unit": FP64_INSTR_PER_UNIT,
+                # what actually bounds the kernel: a warp-wide FP64 instruction holds a sub-partition's dispatch
+                # port for two cycles (16 FP64 lanes), every other instruction for one
+                "dispatch_model": dispatch_model(units_kernel, kernel_ms, clocks),
                 "achieved_def": "FP64-pipe instructions issued per unit (SASS count, profiles/) x units x 2 flop "
                                 "(DFMA-slot equivalents) / CUDA-event kernel time",
                 "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak: constant multiplier/addend, "
