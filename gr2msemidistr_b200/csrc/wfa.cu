@@ -1391,7 +1391,7 @@ static int plan_build_runs(wfa_plan *p)
     const int lc = p->comp_level;
     if (lc >= p->nlevels) return GR2M_OK;
     const int ub = off[lc], nu = p->norder - ub;
-    if (nu <= 0 || nu >= (1 << 28)) return GR2M_OK;
+    if (nu <= 0 || nu >= (1 << 27)) return GR2M_OK;     // sort key bits; stream rows (<= 8 per cell) stay below 2^30
     cudaStream_t st = p->stream;
     const long long n = p->ncell;
     const int nb = ceil_div(nu, 256);
