@@ -185,7 +185,7 @@ __global__ void k_tile_forcing(const double *__restrict__ P, const double *__res
         double pv = ok ? P[(size_t)c * ntime + t] : 0.0, ev = ok ? E[(size_t)c * ntime + t] : 0.0;
         sp[j][lx] = pv;
         se[j][lx] = ev;
-        if (!(fabs(pv) < 1e9 && fabs(ev) < 1e9)) *bad = 1;   // also catches NaN / Inf
+        if (!(fabs(pv) < 1e5 && fabs(ev) < 1e5)) *bad = 1;   // mm per month; also catches NaN / Inf
     }
     __syncthreads();
     for (int j = ly; j < 32; j += 8) {
@@ -233,8 +233,8 @@ __device__ __forceinline__ CellPar load_par(const double *__restrict__ par, int 
     p.cP = 0.1 * p.iX1;
     p.kappa = 60.0 * p.iX1;
     p.area = area;
-    // fast rounding needs |f * x| < 1e14; forcing magnitudes are bounded at upload (forcing_ok)
-    p.thr = (forcing_ok && fabs(p.fp) < 1e5 && fabs(p.fe) < 1e5) ? GR2M_TIE_THR : -1.0;
+    // fast rounding needs |10 f x| < 1e9 (see r_round1); forcing magnitudes are bounded at upload (forcing_ok)
+    p.thr = (forcing_ok && fabs(p.fp) < 1e3 && fabs(p.fe) < 1e3) ? GR2M_TIE_THR : -1.0;   // => |10 f x| < 1e9
     return p;
 }
 
@@ -557,7 +557,7 @@ struct gr2m_basin {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
-    int forcing_ok = 0;   // every |P|, |E| < 1e9 and finite (checked on the device at upload)
+    int forcing_ok = 0;   // every |P|, |E| < 1e5 and finite (checked on the device at upload)
     DevBuf F, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
     double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
     int qobs_n = 0;

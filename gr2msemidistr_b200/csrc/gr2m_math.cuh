@@ -341,9 +341,11 @@ __device__ __forceinline__ double step_fast4(const CellPar &p, double Praw, doub
                                              const double *__restrict__ tab)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
-    double np_ = (double)__double2int_rn(xp10), ne_ = (double)__double2int_rn(xe10);
+    // rint in one conversion-unit instruction (FRND.F64).  thr >= 0 implies |10 f x| < 1e9 (forcing bounded at
+    // upload, factors at parameter load), where ulp(10 f x) is far inside the tie window
+    double np_ = rint(xp10), ne_ = rint(xe10);
     double fp_ = __dsub_rn(xp10, np_), fe_ = __dsub_rn(xe10, ne_);
-    if (!(fabs(fp_) < p.thr) || !(fabs(fe_) < p.thr)) {   // near a decimal tie (or out of range): exact path
+    if (!(fabs(fp_) < p.thr) || !(fabs(fe_) < p.thr)) {   // near a decimal tie (or NaN, or unbounded input): exact path
         np_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fp, Praw)), 10.0);
         ne_ = __dmul_rn(r_round1_exact(__dmul_rn(p.fe, Eraw)), 10.0);
     }
