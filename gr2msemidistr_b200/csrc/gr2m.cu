@@ -51,7 +51,7 @@ struct CachedBlock { void *p; size_t bytes; int dev; };
 std::mutex g_cache_mu;
 std::vector<CachedBlock> g_cache;
 size_t g_cache_bytes = 0;
-constexpr size_t CACHE_MIN_BLOCK = 1ull << 20;      // smaller blocks are cheap to cudaMalloc/cudaFree
+constexpr size_t CACHE_MIN_BLOCK = 256;             // every cudaFree synchronises and can stall for tens of ms
 constexpr size_t CACHE_MAX_BLOCK = 4ull << 30;      // the dense routing buffers are never kept
 constexpr size_t CACHE_MAX_TOTAL = 8ull << 30;
 bool cache_enabled()
@@ -122,11 +122,13 @@ int gr2m_dev_alloc(void **p, size_t bytes, size_t *got)
 void gr2m_dev_free(void *p, size_t bytes)
 {
     if (!p) return;
+    static const bool dbg = getenv("GR2M_CACHE_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[gr2m cache] free %zu bytes, cached %zu bytes in %zu blocks\n", bytes, g_cache_bytes, g_cache.size());
     if (bytes >= CACHE_MIN_BLOCK && bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
         // like cudaFree, nothing may still be using the block when it changes hands
         if (cudaDeviceSynchronize() == cudaSuccess) {
             std::lock_guard<std::mutex> lk(g_cache_mu);
-            if (g_cache_bytes + bytes <= CACHE_MAX_TOTAL && g_cache.size() < 64) {
+            if (g_cache_bytes + bytes <= CACHE_MAX_TOTAL && g_cache.size() < 512) {
                 int dev = 0;
                 cudaGetDevice(&dev);
                 g_cache.push_back({p, bytes, dev});

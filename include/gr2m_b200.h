@@ -71,7 +71,7 @@ typedef struct wfa_plan   wfa_plan;     /* D8 topology plan resident in HBM */
 const char *gr2m_last_error(void);               /* thread-local message of the last failing call */
 int  gr2m_version(void);                         /* ABI version, currently 1 */
 int  gr2m_device_count(void);                    /* number of CUDA devices, 0 if none */
-/* Handles keep up to 8 GB of freed device blocks (1 MB .. 4 GB each) for the next handle, because the
+/* Handles keep up to 8 GB of freed device blocks (up to 4 GB each) for the next handle, because the
  * reference's workflow creates and destroys one per call; this gives them back to the driver. */
 int  gr2m_release_cached_memory(void);
 int  gr2m_set_device(int device);                /* device used by subsequently created handles */
