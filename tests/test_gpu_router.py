@@ -63,6 +63,11 @@ def test_router_matches_dense_and_oracle(capi, oracle, seed, nrow, ncol, nsub):
         with p.router(src, off, cells) as r:
             info = r.info()
             assert 0 < info["nnodes"] <= 2 * nsub and info["nlevels"] >= 1
+            # same node forest as the CPU restatement of the operator
+            from oracle import router_twin
+            op = router_twin.build(d8, src, off, cells)
+            assert info["nnodes"] == len(op["nodes"]) and info["nactive"] == op["nactive"]
+            assert info["ncandidates"] == sum(len(c) for c in op["cand"])
             assert same(r.apply(QS), ref)
             # columns are just columns: months x parameter sets in one call
             QS2 = rng.uniform(0, 50, (nsub, 3 * 37))
