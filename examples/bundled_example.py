@@ -40,5 +40,5 @@ print("routed discharge at each subbasin, 01/1981:", routed["QR"][0])
 # Optim_GR2MSemiDistr(..., RunIni='01/1981', RunEnd='12/2002', WarmUp=36, Parameters=c(1000,1,1,1), ... Max.Functions=1000, 'KGE')
 cal = api.Optim_GR2MSemiDistr(data, roi, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
                               Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                              Max_Functions=20000, Optimization="KGE", ngs=128)
+                              Max_Functions=1000, Optimization="KGE", restarts=64)
 print("calibrated:", cal["Param"], "KGE", cal["Value"], "in", round(cal["elapsed_s"], 2), "s,", cal["evaluations"], "evaluations")

@@ -216,11 +216,14 @@ class _Objective:
 
 def Optim_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters=None, Parameters_Min=None,
                         Parameters_Max=None, Max_Functions=5000, Optimization="NSE", No_Optim=None,
-                        ngs=None, seed=0, flags=0, shard=None):
+                        ngs=5, restarts=8, seed=0, flags=0, shard=None):
     """SCE-UA calibration.  Returns dict(Param, Value) rounded as Optim:232-244.
 
-    The objective is evaluated for a whole SCE-UA generation at once on the GPU (`ngs` complexes evolve
-    in lock-step; see sceua.py); `shard=(rank, world, allgather)` splits each batch across ranks."""
+    `Max_Functions` and `ngs` mean what they mean to rtop::sceua in the reference (evaluation budget and number
+    of complexes of ONE search; ngs = 5 is rtop's default).  The GPU batch is filled by `restarts` independent
+    searches advancing in lock-step, the best of which is returned (restart 0 starts from `Parameters`); the
+    objective is evaluated for all of their candidate points at once (see sceua.py);
+    `shard=(rank, world, allgather)` splits each batch across ranks."""
     from .sceua import sceua_batched
     be = _capi
     if Optimization not in _capi.OF_NAMES:
@@ -252,7 +255,7 @@ def Optim_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters
                      Parameters[fixed], 4 * nreg, flags)
     print(f"Optimizing {Optimization} with SCE-UA")             # Optim:223
     try:
-        res = sceua_batched(obj, x0, lower, upper, maxn=Max_Functions, ngs=ngs, seed=seed, shard=shard)
+        res = sceua_batched(obj, x0, lower, upper, maxn=Max_Functions, ngs=ngs, restarts=restarts, seed=seed, shard=shard)
     finally:
         obj.close()
     fo = rround(res["value"], 3) if Optimization == "RMSE" else rround(1.0 - res["value"], 3)   # Optim:232-236

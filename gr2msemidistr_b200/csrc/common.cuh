@@ -39,6 +39,16 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 int gr2m_dev_alloc(void **p, size_t bytes, size_t *got);
 void gr2m_dev_free(void *p, size_t bytes);
 
+// A handle that gives back many buffers at once synchronises the device once instead of once per buffer:
+// while a FreeBatch is alive on the calling thread, gr2m_dev_free() skips its own synchronisation.
+struct FreeBatch {
+    bool ok;
+    FreeBatch();
+    ~FreeBatch();
+    FreeBatch(const FreeBatch &) = delete;
+    FreeBatch &operator=(const FreeBatch &) = delete;
+};
+
 // grow-only device buffer owned by a handle (capacity kept across calls)
 struct DevBuf {
     void *p = nullptr;

@@ -21,8 +21,11 @@
 // ---------------------------------------------------------------------------------------------
 // error plumbing / device selection
 // ---------------------------------------------------------------------------------------------
+// Both per host thread, like the CUDA runtime's own current device: a thread that never called
+// gr2m_set_device() works on device 0 and reads its own last error.
 static thread_local char g_err[512] = "";
-static int g_device = 0;
+static thread_local int g_device = 0;
+static thread_local int g_free_batch = 0;   // > 0: a FreeBatch on this thread has already synchronised the device
 
 void gr2m_set_error(const char *fmt, ...)
 {
@@ -125,8 +128,9 @@ void gr2m_dev_free(void *p, size_t bytes)
     static const bool dbg = getenv("GR2M_CACHE_DEBUG") != nullptr;
     if (dbg) fprintf(stderr, "[gr2m cache] free %zu bytes, cached %zu bytes in %zu blocks\n", bytes, g_cache_bytes, g_cache.size());
     if (bytes >= CACHE_MIN_BLOCK && bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
-        // like cudaFree, nothing may still be using the block when it changes hands
-        if (cudaDeviceSynchronize() == cudaSuccess) {
+        // like cudaFree, nothing may still be using the block when it changes hands (a handle that releases
+        // many buffers synchronises once, see FreeBatch)
+        if (g_free_batch > 0 || cudaDeviceSynchronize() == cudaSuccess) {
             std::lock_guard<std::mutex> lk(g_cache_mu);
             if (g_cache_bytes + bytes <= CACHE_MAX_TOTAL && g_cache.size() < 512) {
                 int dev = 0;
@@ -139,6 +143,9 @@ void gr2m_dev_free(void *p, size_t bytes)
     }
     cudaFree(p);
 }
+
+FreeBatch::FreeBatch() : ok(cudaDeviceSynchronize() == cudaSuccess) { if (ok) ++g_free_batch; }
+FreeBatch::~FreeBatch() { if (ok) --g_free_batch; }
 
 extern "C" int gr2m_release_cached_memory(void)
 {
@@ -360,8 +367,11 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
             }
             __syncwarp();
             if (lane == 0) {
-                // this warp's reads of the stage are complete (their values were consumed above)
+                // this warp's reads of the stage are complete (their values were consumed above); the fences
+                // order them before the count and the count before the refill (release / acquire on left[st])
+                __threadfence_block();
                 if (atomicAdd(&left[st], 1) == SPB - 1) {
+                    __threadfence_block();
                     left[st] = 0;
                     const int gn = g + NST2;
                     if (gn < total) {
@@ -504,8 +514,11 @@ __global__ void __launch_bounds__(128) k_objective(ObjArgs a)
             rmse = sqrt(mse);
             if (n > 1.0) {
                 double sd_s = sqrt(vs / (n - 1.0)), sd_o = sqrt(vo / (n - 1.0));
+                // cor() clamps to [-1, 1] and is NA when either standard deviation is 0; the comparisons keep a
+                // NaN (fmin/fmax would return the other operand and turn it into r = -1)
                 double r = cv / (sqrt(vs) * sqrt(vo));
-                r = fmin(fmax(r, -1.0), 1.0);
+                if (r > 1.0) r = 1.0;
+                if (r < -1.0) r = -1.0;
                 double alpha = sd_s / sd_o, beta = ms / mo;
                 if (mo != 0.0 || sd_o != 0.0) {
                     double x = r - 1.0, y = alpha - 1.0, z = beta - 1.0;
@@ -555,7 +568,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
 // ---------------------------------------------------------------------------------------------
 
 struct gr2m_basin {
-    int device = 0, ntime = 0, ntime_pad = 0, ncell = 0, ncell_pad = 0, ntiles = 0, nreg = 0;
+    int device = 0, sm_count = 0, ntime = 0, ntime_pad = 0, ncell = 0, ncell_pad = 0, ntiles = 0, nreg = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -569,6 +582,7 @@ static void basin_free(gr2m_basin *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
+    FreeBatch fb;
     DevBuf *bufs[] = {&b->F, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
                       &b->crit, &b->qobs, &b->sim_out, &b->sim_t, &b->s0, &b->r0, &b->send, &b->rend};
     for (DevBuf *d : bufs) d->release();
@@ -754,17 +768,11 @@ extern "C" int gr2m_run_once(int ntime, int ncell, const double *P, const double
     return rc;
 }
 
-static int g_sm_count = 0;
-
 static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, const double *qobs, int warmup,
                             int which, int flags, double *of_dev, double *crit_dev, double *qt_dev)
 {
     int rc;
-    if (!g_sm_count) {
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, b->device));
-        g_sm_count = prop.multiProcessorCount;
-    }
+    if (!b->sm_count) CK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
     // qobs -> device (cached: re-uploaded only when the host values change)
     const bool has_obs = qobs != nullptr;
     if (has_obs) {
@@ -783,7 +791,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     }
     // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
     const int nsg = ceil_div(nsets, SPB);
-    const int target = g_sm_count * 4 * 8;
+    const int target = b->sm_count * 4 * 8;
     int csplit = ceil_div(target, nsg);
     if (csplit > b->ntiles) csplit = b->ntiles;
     if (csplit < 1) csplit = 1;

@@ -249,7 +249,7 @@ static void router_free(wfa_router *r)
     cudaSetDevice(r->device);
     DevBuf *bufs[] = {&r->node_src, &r->child_off, &r->child_idx, &r->horder, &r->cand_off, &r->cand_idx, &r->haszero,
                       &r->qs, &r->val, &r->qr};
-    for (DevBuf *d : bufs) d->release();
+    { FreeBatch fb; for (DevBuf *d : bufs) d->release(); }
     delete r;
 }
 
@@ -265,6 +265,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
     auto cleanup = [&]() {
         DevBuf *t[] = {&src, &poff, &pcells, &srcmap, &act, &acells, &nsel, &temp, &isnode, &rank, &node_cell, &parent,
                        &ckey, &ckey2, &cval, &cval2, &ccnt, &height, &hkey2, &hist, &flag, &key, &ksel, &ksort, &kuniq};
+        FreeBatch fb;
         for (DevBuf *d : t) d->release();
     };
 #define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)

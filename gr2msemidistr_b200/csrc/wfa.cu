@@ -1158,7 +1158,7 @@ static void plan_free(wfa_plan *p)
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
                       &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx, &p->rcell, &p->rup_off,
                       &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo, &p->rdone};
-    for (DevBuf *d : bufs) d->release();
+    { FreeBatch fb; for (DevBuf *d : bufs) d->release(); }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->evm) cudaEventDestroy(p->evm);
@@ -1400,6 +1400,7 @@ static int plan_build_runs(wfa_plan *p)
     auto cleanup = [&]() {
         DevBuf *t[] = {&upos, &pred, &npu, &h0, &h1, &d0, &d1, &rl, &flag, &keys, &keys2, &vals, &sj, &temp, &isstart,
                        &rank, &cnt, &runrl};
+        FreeBatch fb;
         for (DevBuf *d : t) d->release();
     };
 #define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)

@@ -55,3 +55,81 @@ def test_zonal_mean_weights_follow_coverage():
     assert abs(m[0, 0] - (1 + 4 + 5) / 3) < 1e-9 and abs(m[0, 1] - 1.0) < 1e-12    # nodata cell ignored
     w = gis.zonal_weights(r, [poly], 0.1)
     assert w[0, 0] == w[1, 1] == 100 and w[2, 3] == 0
+
+
+def test_coverage_fractions_hand_computed():
+    # unit grid, north-west corner (0, 4), 4 x 4 cells; row 0 is y in [3, 4]
+    def cov(*rings):
+        return gis.coverage_fractions([np.array(r, float) for r in rings], 0.0, 4.0, 1.0, 1.0, 4, 4)
+    # axis-aligned rectangle [0.5, 2.25] x [1, 3.5]
+    c = cov([[0.5, 1], [2.25, 1], [2.25, 3.5], [0.5, 3.5], [0.5, 1]])
+    want = np.zeros((4, 4))
+    want[0, :3] = [0.25, 0.5, 0.125]          # y in [3, 3.5]: half a row
+    want[1, :3] = want[2, :3] = [0.5, 1.0, 0.25]
+    assert np.allclose(c, want, atol=1e-15)
+    # right triangle (0,0) (4,0) (0,4): cells on the diagonal are half covered, below it full
+    t = cov([[0, 0], [4, 0], [0, 4], [0, 0]])
+    for r in range(4):
+        for col in range(4):
+            below = col + (3 - r) < 3
+            on = col + (3 - r) == 3
+            assert abs(t[r, col] - (1.0 if below else 0.5 if on else 0.0)) < 1e-15
+    assert abs(t.sum() - 8.0) < 1e-14
+    # clockwise orientation gives the same fractions
+    assert np.allclose(cov([[0, 0], [0, 4], [4, 0], [0, 0]]), t, atol=1e-15)
+    # a hole (opposite orientation) is subtracted; a hole strictly inside one cell leaves that cell partial
+    h = cov([[0, 0], [0, 4], [4, 4], [4, 0], [0, 0]], [[1.25, 1.25], [1.75, 1.25], [1.75, 1.75], [1.25, 1.75], [1.25, 1.25]])
+    assert abs(h[2, 1] - 0.75) < 1e-15 and abs(h.sum() - 15.75) < 1e-14
+    # two parts
+    m = cov([[0, 0], [0, 1.5], [1.5, 1.5], [1.5, 0], [0, 0]], [[3, 3], [3, 4], [4, 4], [4, 3], [3, 3]])
+    assert abs(m.sum() - 3.25) < 1e-14 and m[0, 3] == 1.0 and abs(m[2, 1] - 0.25) < 1e-15
+    # polygon reaching outside the grid: only the part on the grid counts
+    o = cov([[-2, -2], [2.5, -2], [2.5, 0.5], [-2, 0.5], [-2, -2]])
+    assert np.allclose(o[3], [0.5, 0.5, 0.25, 0.0]) and o[:3].sum() == 0.0
+
+
+def test_coverage_fractions_match_dense_sampling(rng=np.random.default_rng(3)):
+    # an irregular concave polygon against 400 x 400 sub-samples per cell
+    ang = np.sort(rng.uniform(0, 2 * np.pi, 23))
+    rad = rng.uniform(1.0, 3.4, 23)
+    ring = np.column_stack([3.6 + rad * np.cos(ang), 3.4 + rad * np.sin(ang)])
+    ring = np.vstack([ring, ring[:1]])
+    c = gis.coverage_fractions([ring], 0.0, 7.0, 1.0, 1.0, 8, 7)
+    assert abs(c.sum() - abs(gis.ring_area(ring))) < 1e-12            # fractions add up to the polygon's area
+    n = 400
+    u = (np.arange(n) + 0.5) / n
+    for (r, col) in [(3, 3), (1, 4), (5, 2), (3, 6), (0, 3)]:
+        X, Y = np.meshgrid(col + u, 7.0 - r - u)
+        assert abs(gis.points_in_polygon(X, Y, [ring]).mean() - c[r, col]) < 5e-3
+    inner = gis.interior_cells(gis.Raster(np.zeros((1, 7, 8), np.float32), 0.0, 7.0, 1.0, 1.0), [ring])
+    assert sorted(inner.tolist()) == sorted(np.flatnonzero(c.reshape(-1) == 1.0).tolist())
+
+
+def test_zonal_weights_nested_and_general_grids_agree():
+    r = gis.Raster(np.zeros((1, 6, 6), np.float32), 10.0, 6.0, 1.0, 1.0)
+    ring = np.array([[10.3, 0.7], [15.2, 1.1], [14.1, 5.6], [11.9, 4.2], [10.3, 0.7]])
+    nested = gis.zonal_weights(r, [ring], 0.1)                         # 10 x 10 fine cells per source cell
+    assert abs(nested.sum() / 100.0 - abs(gis.ring_area(ring))) < 1e-12
+    # same fine grid through the general (non-nested) branch: 0.1 * (1 + 1e-5) does not divide the cell size
+    general = gis.zonal_weights(r, [ring], 0.1 * (1 + 1e-5))
+    assert np.max(np.abs(general - nested)) < 0.25                     # < a quarter fine cell anywhere
+    # crop window (Create:95): cells outside the window carry no weight
+    win = gis.crop_window(r, [[ring]], 1.0)                            # bbox snapped to the nearest cell edges
+    assert win == (0, 5, 0, 5)
+    cropped = gis.zonal_weights(r, [ring], 0.1, win)
+    assert cropped[:, 5].sum() == 0.0 and cropped[5].sum() == 0.0 and np.array_equal(cropped[:5, :5], nested[:5, :5])
+
+
+def test_point_on_surface_multipart_uses_the_widest_part():
+    # shapefile orientation: shells clockwise, holes counter-clockwise
+    small = np.array([[0, 0], [0, 1], [1, 1], [1, 0], [0, 0]], float)
+    big = np.array([[10, 0], [10, 6], [18, 6], [18, 0], [10, 0]], float)
+    hole = np.array([[12, 2], [16, 2], [16, 4], [12, 4], [12, 2]], float)
+    assert gis.ring_area(small) < 0 < gis.ring_area(hole)
+    parts = gis.split_parts([small, big, hole])
+    assert len(parts) == 2 and len(parts[0]) == 1 and len(parts[1]) == 2
+    x, y = gis.point_on_surface([small, big, hole])
+    # the big part's scan line (y = 3: midway between the vertex ordinates 2 and 4 that bracket the envelope's
+    # centre) crosses 10..12 and 16..18, both 2 wide -- wider than anything in the small part
+    assert gis.points_in_polygon(np.array([x]), np.array([y]), [big, hole])[0]
+    assert (x, y) == (11.0, 3.0)

@@ -159,7 +159,7 @@ def test_optim_wrapper_with_stub_backend(c1):
     data, sb = _frame(inp), _subbasins(inp)
     res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=400, Optimization="KGE", ngs=4)
+                                  Max_Functions=400, Optimization="KGE", ngs=4, restarts=1)
     assert res["Param"].shape == (4,) and np.array_equal(res["Param"], rround(res["Param"], 3))
     assert np.all(res["Param"] >= [1, 0.01, 0.8, 0.8]) and np.all(res["Param"] <= [2000, 2, 1.2, 1.2])
     with backend_stub.Basin(inp["P"][:, :264], inp["E"][:, :264], inp["area"], inp["ndays"][:264], np.zeros(13, np.int32), 1) as b:
@@ -187,6 +187,6 @@ def test_optim_fixed_regions_are_spliced_back(oracle):
     start = np.array([1000.0, 800.0, 1.0, 1.1, 1.0, 0.9, 1.0, 1.05])
     res = api.Optim_GR2MSemiDistr(pd.DataFrame(cols), sb, "01/1981", "12/1985", WarmUp=12, Parameters=start,
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=1500, Optimization="RMSE", No_Optim=["B"], ngs=6)
+                                  Max_Functions=1500, Optimization="RMSE", No_Optim=["B"], ngs=6, restarts=1)
     assert np.array_equal(res["Param"][[1, 3, 5, 7]], truth[[1, 3, 5, 7]])
     assert res["Value"] < 5.0

@@ -108,11 +108,14 @@ def test_calibration_on_the_gpu(capi, c1, monkeypatch):
     data, sb = _frame(inp), _subbasins(inp)
     res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", WarmUp=36, Parameters=[1000, 1, 1, 1],
                                   Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
-                                  Max_Functions=20000, Optimization="KGE", ngs=128)
-    # same search with the oracle evaluating the objective: identical trajectory unless an objective
+                                  Optimization="KGE", restarts=223)
+    # BASELINE config C2 as quoted: 223 lock-step searches x 5 complexes x 9 points = 10 035 candidate sets in the
+    # first batch and ~1e4 - 3e4 per generation (9 CCE rounds of up to three 1 115-point batches), each search
+    # with the reference's own budget (Max.Functions = 5000, ngs = 5; Optim:49, 225-229).
+    # Same search with the oracle evaluating the objective: identical trajectory unless an objective
     # value differs in its third decimal, so the optimum agrees to the quantisation of Optim:210
     ref = _with_stub(monkeypatch, api.Optim_GR2MSemiDistr, data, sb, "01/1981", "12/2002", WarmUp=36,
                      Parameters=[1000, 1, 1, 1], Parameters_Min=[1, 0.01, 0.8, 0.8],
-                     Parameters_Max=[2000, 2, 1.2, 1.2], Max_Functions=3000, Optimization="KGE", ngs=16)
-    assert res["Value"] >= ref["Value"] - 0.02 and res["Value"] > 0.5
-    assert res["evaluations"] > 5000          # whole generations of 128 complexes x 9 points per batch
+                     Parameters_Max=[2000, 2, 1.2, 1.2], Max_Functions=3000, Optimization="KGE", restarts=2)
+    assert res["Value"] >= ref["Value"] - 0.005 and res["Value"] > 0.5
+    assert res["evaluations"] > 223 * 1000

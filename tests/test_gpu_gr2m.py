@@ -142,20 +142,24 @@ def _check_objective(capi, oracle, P, E, area, nd, region, nreg, par, warmup, fl
     ok = np.isfinite(ref_u["crit"])
     assert np.array_equal(np.isfinite(unr["crit"]), ok)
     assert relerr(unr["crit"][ok], ref_u["crit"][ok]) <= TOL
-    # rounded path (Optim:195, 210-212): identical except where a sum sits on a rounding tie
+    # rounded path (Optim:195, 210-212): identical except where a sum sits on a rounding tie.  A value lands
+    # within the 1e-13 parity margin of a tie with probability ~1e-11 (sink, quantum 0.01) / ~1e-10 (criterion,
+    # quantum 0.001); measured: 0 of 2.64 M sink values and 0 of 30 000 criteria (profiles/r1_parity_margins.jsonl),
+    # so the bound is "at most one quantum, at most 1e-5 / 1e-4 of the values"
     dq = np.abs(rnd[1]["qt"] - ref_r["qt"])
-    assert np.all(dq <= 0.01 + 1e-9) and np.mean(dq > 1e-9) < 1e-4
+    assert np.all(dq <= 0.01 + 1e-9) and np.mean(dq > 1e-9) <= 1e-5
     for w in (0, 1, 2):
         d = np.abs(rnd[w]["of"] - ref_r["of"][:, w])
         okw = np.isfinite(ref_r["of"][:, w])
-        assert np.all(d[okw] <= 1e-3 + 1e-9) and np.mean(d[okw] > 1e-9) <= 0.01
+        assert np.array_equal(np.isfinite(rnd[w]["of"]), okw)
+        assert np.all(d[okw] <= 1e-3 + 1e-9) and np.mean(d[okw] > 1e-9) <= 1e-4
     assert abs(one["of"][0] - rnd[0]["of"][1]) == 0.0
 
 
 def test_objective_c2_shape(capi, oracle):
-    # config C2: 13 subbasins x 264 months (WarmUp 36) x many candidate sets (2 000 here; the oracle is serial)
+    # config C2 as quoted: 13 subbasins x 264 months (WarmUp 36) x 10^4 candidate sets in one batch
     P, E, area, nd = synth.forcing(13, 264)
-    _check_objective(capi, oracle, P, E, area, nd, np.zeros(13, np.int32), 1, synth.param_sets(2000), 36)
+    _check_objective(capi, oracle, P, E, area, nd, np.zeros(13, np.int32), 1, synth.param_sets(10000), 36)
 
 
 def test_objective_multi_tile_multi_region(capi, oracle, rng):
@@ -233,3 +237,44 @@ def test_large_sweep_properties(capi):
         q2 = b.objective_batch(par, None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
     assert relerr(q2, q0) <= 1e-12
     assert np.all(np.isfinite(q0)) and np.all(q0 >= 0)
+
+
+def test_objective_degenerate_series_match_oracle(capi, oracle):
+    """hydroGOF's undefined cases (R/Optim_GR2MSemiDistr.R:209-212): a criterion that is NA in R (cor() with a
+    zero standard deviation, sd() of one value, a zero NSE denominator, no pairs left by na.omit) must be NaN
+    on the device too -- the first build clamped a NaN correlation to -1 and returned a finite KGE."""
+    ncell, ntime, wu = 40, 72, 12
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=71)
+    region = np.zeros(ncell, np.int32)
+    par = np.vstack([synth.param_sets(13, seed=72), [[np.nan, 0.5, 1.0, 1.0], [300.0, np.nan, 1.0, 1.0], [300.0, 0.5, np.nan, 1.0]]])
+    base = oracle.run(P, E, area, nd, region, 1, par[0])
+    good = synth.qobs_from(oracle.outlet_optim(base["QS"]))
+    one_pair = np.full(ntime, np.nan); one_pair[40] = 17.25
+    two_pairs = one_pair.copy(); two_pairs[41] = 3.5
+    only_warmup = np.full(ntime, np.nan); only_warmup[:wu] = 5.0
+    cases = {
+        "regular": (area, good),
+        "constant sim (areas so small that round(sum, 2) = 0)": (area * 1e-9, good),
+        "constant obs": (area, np.full(ntime, 42.0)),
+        "all-zero obs": (area, np.zeros(ntime)),
+        "one valid pair": (area, one_pair),
+        "two valid pairs": (area, two_pairs),
+        "no valid pair": (area, np.full(ntime, np.nan)),
+        "valid pairs only inside the warm-up": (area, only_warmup),
+    }
+    for name, (ar, qobs) in cases.items():
+        for fl in (0, capi.SINK_UNROUNDED):
+            ref = oracle.objective_batch(P, E, ar, nd, region, 1, par, qobs, wu, flags=oracle.SINK_UNROUNDED if fl else 0, nthreads=4)
+            with capi.Basin(P, E, ar, nd, region, 1) as b:
+                got = {w: b.objective_batch(par, qobs, wu, w, fl, want_qt=True) for w in (0, 1, 2)}
+            nan_ref = np.isnan(ref["crit"])
+            assert np.array_equal(np.isnan(got[0]["crit"]), nan_ref), name
+            assert np.array_equal(np.isnan(got[0]["qt"]), np.isnan(ref["qt"])), name
+            assert relerr(got[0]["crit"][~nan_ref], ref["crit"][~nan_ref]) <= TOL, name
+            for w in (0, 1, 2):      # the value SCE-UA minimises: NaN exactly where R's is NA
+                assert np.array_equal(np.isnan(got[w]["of"]), np.isnan(ref["of"][:, w])), (name, w)
+    # sanity of the cases themselves (so the test cannot pass vacuously)
+    ref = oracle.objective_batch(P, E, area * 1e-9, nd, region, 1, par[:2], good, wu)
+    assert np.all(ref["qt"] == 0.0) and np.all(np.isnan(ref["crit"][:, 0])) and np.all(np.isfinite(ref["crit"][:, 1:]))
+    ref = oracle.objective_batch(P, E, area, nd, region, 1, par[:2], np.full(ntime, 42.0), wu)
+    assert np.all(np.isnan(ref["crit"][:, :2])) and np.all(np.isfinite(ref["crit"][:, 2]))

@@ -70,3 +70,34 @@ def test_objective_batch_equals_run_plus_gof(oracle, rng):
     res1 = oracle.objective_batch(P[:1], E[:1], area[:1], nd, region[:1], 1, par, qobs, warmup=12)
     r1 = oracle.run(P[:1], E[:1], area[:1], nd, region[:1], 1, par[2])
     assert np.array_equal(res1["qt"][2], r1["QS"][0])
+
+
+def test_degenerate_cases_follow_hydrogof(oracle):
+    """hydroGOF on degenerate series (R/Optim_GR2MSemiDistr.R:209-212 calls KGE/NSE/rmse on what na.omit
+    leaves): cor() is NA when either standard deviation is 0, sd() is NA for one value, NSE is NA when
+    obs is constant, everything is NA with no pairs."""
+    nan = np.nan
+    obs = np.array([3.0, 5.0, 4.0, 9.0, 1.0])
+    # constant simulated series: sd(sim) = 0 -> cor NA -> KGE NA; NSE and rmse stay finite
+    n, crit, of = oracle.gof(np.full(5, 2.0), obs)
+    assert n == 5 and np.isnan(crit[0]) and np.isfinite(crit[1]) and np.isfinite(crit[2])
+    assert np.isnan(of[0]) and np.isfinite(of[1]) and np.isfinite(of[2])
+    # constant observed series: cor NA and the NSE denominator is 0 -> both NA; rmse finite
+    n, crit, _ = oracle.gof(obs, np.full(5, 2.0))
+    assert n == 5 and np.isnan(crit[0]) and np.isnan(crit[1]) and abs(crit[2] - np.sqrt(np.mean((obs - 2.0) ** 2))) < 1e-15
+    # all-zero observations: mean 0 and sd 0 -> the KGE guard itself says NA
+    _, crit, _ = oracle.gof(obs, np.zeros(5))
+    assert np.isnan(crit[0]) and np.isnan(crit[1])
+    # one valid pair: sd() of one value is NA, NSE denominator 0; rmse = |d|
+    n, crit, _ = oracle.gof(np.array([1.0, 2.0, 3.0]), np.array([nan, 2.5, nan]))
+    assert n == 1 and np.isnan(crit[0]) and np.isnan(crit[1]) and crit[2] == 0.5
+    # no valid pair at all
+    n, crit, of = oracle.gof(np.array([1.0, 2.0]), np.array([nan, nan]))
+    assert n == 0 and np.all(np.isnan(crit)) and np.all(np.isnan(of))
+    # NaN simulation (NaN parameters): rows dropped by na.omit like NA observations
+    n, crit, _ = oracle.gof(np.full(4, nan), obs[:4])
+    assert n == 0 and np.all(np.isnan(crit))
+    # twin agrees on which criteria are defined
+    for sim, o in ((np.full(5, 2.0), obs), (obs, np.full(5, 2.0)), (obs, np.zeros(5))):
+        tc, _ = twin.gof(sim, o)
+        assert np.array_equal(np.isnan(tc), np.isnan(oracle.gof(sim, o)[1]))
