@@ -277,6 +277,7 @@ struct CalibArgs {
     const double *F, *area, *params, *tconv;   // tconv: conv[t] (fast) or den[t] (literal)
     const int *region;
     double *partial;                           // [csplit][nsets][ntime]
+    const double *frange;                      // per cell max P, max E (k_cell_range); table-mode kernel only
     int ncell, ntiles, ntime, ntime_pad, nreg, nsets, nsg, tiles_per_split, f32exp, forcing_ok;
 };
 
@@ -387,6 +388,8 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
         for (int t = lane; t < a.ntime; t += 32)
             a.partial[((size_t)cs * a.nsets + set) * a.ntime + t] = myacc[t];
 }
+
+#include "gr2m_calib3.cuh"
 
 struct SimArgs {
     const double *F, *area, *params, *den, *S0, *R0;
@@ -573,7 +576,7 @@ struct gr2m_basin {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int forcing_ok = 0;   // every |P|, |E| < 1e5 and finite (checked on the device at upload)
-    DevBuf F, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
+    DevBuf F, frange, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
     double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
     int qobs_n = 0;
 };
@@ -583,7 +586,7 @@ static void basin_free(gr2m_basin *b)
     if (!b) return;
     cudaSetDevice(b->device);
     FreeBatch fb;
-    DevBuf *bufs[] = {&b->F, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
+    DevBuf *bufs[] = {&b->F, &b->frange, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
                       &b->crit, &b->qobs, &b->sim_out, &b->sim_t, &b->s0, &b->r0, &b->send, &b->rend};
     for (DevBuf *d : bufs) d->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
@@ -622,6 +625,7 @@ static int basin_create_common(int ntime, int ncell, const double *P, const doub
     BCU(cudaEventCreate(&b->ev1));
     size_t nraw = (size_t)ncell * ntime * sizeof(double);
     BCK(b->F.ensure((size_t)b->ntiles * b->ntime_pad * 64 * sizeof(double)));
+    BCK(b->frange.ensure((size_t)ncell * 2 * sizeof(double)));
     BCK(b->area.ensure(ncell * sizeof(double)));
     BCK(b->region.ensure(ncell * sizeof(int)));
     BCK(b->den.ensure(ntime * sizeof(double)));
@@ -649,6 +653,9 @@ static int basin_create_common(int ntime, int ncell, const double *P, const doub
         int *bad = reinterpret_cast<int *>(b->conv.as<char>() + (size_t)ntime * sizeof(double));
         step(cudaMemsetAsync(bad, 0, sizeof(int), b->stream));
         k_tile_forcing<<<grid, blk, 0, b->stream>>>(Pd, Ed, ncell, ntime, b->ntime_pad, b->F.as<double>(), bad);
+        step(cudaGetLastError());
+        k_cell_range<<<ceil_div(ncell, 128), 128, 0, b->stream>>>(b->F.as<double>(), ncell, ntime, b->ntime_pad,
+                                                                  b->frange.as<double>());
         step(cudaGetLastError());
         int hbad = 1;
         step(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -811,15 +818,30 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
     a.forcing_ok = b->forcing_ok;
-    size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + CALIB_TAB) * sizeof(double) + NST2 * 12;
-    REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
-    auto kern = fast ? (a.f32exp ? k_gr2m_calib2<true, true> : k_gr2m_calib2<true, false>)
-                     : (a.f32exp ? k_gr2m_calib2<false, true> : k_gr2m_calib2<false, false>);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaEventRecord(b->ev0, b->stream));
-    kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(b->ev1, b->stream));
+    a.frange = b->frange.as<double>();
+    // one region: per-set power tables (gr2m_calib3.cuh); several regions: a lane's X1 depends on its cell
+    static const bool no_tab = getenv("GR2M_CALIB_GENERIC") != nullptr;
+    if (fast && b->nreg == 1 && !no_tab) {
+        const size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * SPB * 32) * sizeof(double) + NST2 * 12;
+        static const int ctas = getenv("GR2M_CALIB3_CTAS") ? atoi(getenv("GR2M_CALIB3_CTAS")) : 3;   // experiment switch
+        auto kern = a.f32exp ? k_gr2m_calib3<true, 3> : (ctas == 2 ? k_gr2m_calib3<false, 2> : ctas == 4 ? k_gr2m_calib3<false, 4> : k_gr2m_calib3<false, 3>);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaEventRecord(b->ev0, b->stream));
+        CK(cudaMemsetAsync(b->partial.p, 0, (size_t)csplit * nsets * b->ntime * sizeof(double), b->stream));
+        kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev1, b->stream));
+    } else {
+        const size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * b->ntime_pad + b->ntime_pad + CALIB_TAB) * sizeof(double) + NST2 * 12;
+        REQUIRE(smem <= 200 * 1024, "ntime too large for the shared-memory outlet accumulators");
+        auto kern = fast ? (a.f32exp ? k_gr2m_calib2<true, true> : k_gr2m_calib2<true, false>)
+                         : (a.f32exp ? k_gr2m_calib2<false, true> : k_gr2m_calib2<false, false>);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaEventRecord(b->ev0, b->stream));
+        kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev1, b->stream));
+    }
     ObjArgs o;
     o.partial = b->partial.as<double>(); o.qobs = has_obs ? b->qobs.as<double>() : nullptr;
     o.qt = qt_dev; o.of = of_dev; o.crit = crit_dev;

@@ -1,0 +1,231 @@
+// gr2m_calib3.cuh -- calibration-mode recursion with per-set power tables (included by gr2m.cu).
+//
+// In calibration mode the corrected forcing is n/10 with n = rint(10 f x) an integer (R's round(f*x, 1),
+// R/Run_GR2MSemiDistr.R:101-102), and with one region all lanes of a warp share X1, so both exponentials of a
+// month are exp(n c) with ONE c = 0.2/X1 per warp:  exp(n c) = exp(256 i c) * exp(j c),  n = 256 i + j.
+// Each warp builds T1h[i] = exp(min(256 i c, 26))/2 and T2[j] = exp(j c) (2 x 256 doubles, 4 KiB) once and a
+// month's exp becomes two shared-memory reads and one DMUL instead of 8 FP64-pipe instructions and a clamp
+// (airGR's min(WS, 13) is an integer min on n).  A tile where some lane could see n outside [0, 65535] (huge
+// forcing with a large X1, negative forcing or factors, unbounded input) or whose set has X1 < 1 (c > 0.2: the
+// clamped argument n_clamp c could overshoot 26 by more than 0.2) takes step_fast4, the general formulation.
+// Outlet sums go to global memory by fire-and-forget FP64 reductions (RED.ADD.F64): every (set, month) word is
+// only ever updated by one lane of one warp, in program order, so the sums are deterministic; this frees the
+// 30 KiB of per-CTA accumulators and lets the tables in.
+#pragma once
+
+constexpr int PT_N = 256;                 // entries per table level
+constexpr int PT_WARP_DBL = 2 * PT_N;     // doubles per warp
+
+// per cell: frange[2c] = max_t P, frange[2c+1] = max_t E; +inf when any value is negative or not finite
+__global__ void k_cell_range(const double *__restrict__ F, int ncell, int ntime, int ntime_pad, double *__restrict__ frange)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    const double *f = F + (size_t)(cell >> 5) * ntime_pad * 64 + (cell & 31);
+    double pm = 0.0, em = 0.0;
+    bool bad = false;
+    for (int t = 0; t < ntime; ++t) {
+        double p = f[(size_t)t * 64], e = f[(size_t)t * 64 + 32];
+        bad |= !(p >= 0.0) || !(e >= 0.0);
+        pm = fmax(pm, p);
+        em = fmax(em, e);
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    frange[2 * cell] = bad ? inf : pm;
+    frange[2 * cell + 1] = bad ? inf : em;
+}
+
+// Table-mode month step: same algebra as step_fast4 (gr2m_math.cuh), exponentials from the warp's tables.
+// t1 / t2: shared-memory byte addresses of the warp's T1h / T2; nclamp: smallest n with n c >= 26.
+// exp(n c)/2 from the warp's tables: T1h[n >> 8] * T2[n & 255]; addresses by one shift / mask and one multiply-add each
+__device__ __forceinline__ double pow_tab_half(int n, uint32_t t1, uint32_t t2)
+{
+    uint32_t a1, a2;
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a1) : "r"((uint32_t)n >> 8), "r"(t1));
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a2) : "r"((uint32_t)n & (PT_N - 1)), "r"(t2));
+    double h, l;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(h) : "r"(a1));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(l) : "r"(a2));
+    return __dmul_rn(h, l);
+}
+
+// The part of a month that does not depend on the rounding decision's branch: stores, percolation, routing.
+template <bool F32EXP>
+__device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, double a2, double b2, double &s, double &rho)
+{
+    double am = a2 - 0.5, ap = a2 + 0.5;
+    double s1 = div_fast3(__fma_rn(s, ap, am), __fma_rn(s, am, ap));
+    // (b2 + 1/2) + (1 - s1)(b2 - 1/2) = b2 (2 - s1) + s1/2: one FP64 instruction less
+    double s2 = div_fast3(s1, __fma_rn(b2, 2.0 - s1, 0.5 * s1));
+    double c = __fma_rn(s2 * s2, s2, 1.0);
+    double y = rcbrt_fast(c);
+    if (F32EXP) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
+    double sn = s2 * y;
+    double d = (s - s1) + (s2 - sn);
+    double rho2 = p.X2 * (__fma_rn(np_, p.cP, rho) + d);
+    double q = div_fast3(rho2 * rho2, rho2 + p.kappa);
+    rho = rho2 - q;
+    s = sn;
+    return q;
+}
+
+// Table-mode month, branch-free: the rounding decision is rint(10 f x); `tie` collects the lanes that were within
+// 1e-8 of a decimal tie (|10 f x| < 2^16 here, ulp <= 1.5e-11: R's candidate comparison cannot disagree with rint
+// outside that window).  The caller repeats the 8-month chunk with step_tab when any lane raised it.
+template <bool F32EXP>
+__device__ __forceinline__ double step_tab_nb(const CellPar &p, double Praw, double Eraw, double &s, double &rho,
+                                              uint32_t t1, uint32_t t2, int nclamp, bool &tie)
+{
+    double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
+    double np_ = rint(xp10), ne_ = rint(xe10);
+    int ip = __double2int_rn(xp10), ie = __double2int_rn(xe10);
+    const bool okp = fabs(__dsub_rn(xp10, np_)) < KC.tie_thr_tab, oke = fabs(__dsub_rn(xe10, ne_)) < KC.tie_thr_tab;
+    tie |= !(okp & oke);
+    const double a2 = pow_tab_half(min(ip, nclamp), t1, t2);
+    const double b2 = pow_tab_half(min(ie, nclamp), t1, t2);
+    return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
+}
+
+// Same month with the exact rounding path taken by the lanes that need it (R's candidate comparison).
+template <bool F32EXP>
+__device__ __forceinline__ double step_tab(const CellPar &p, const double *__restrict__ par, double Praw, double Eraw,
+                                           double &s, double &rho, uint32_t t1, uint32_t t2, int nclamp)
+{
+    double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
+    double np_ = rint(xp10), ne_ = rint(xe10);
+    int ip = __double2int_rn(xp10), ie = __double2int_rn(xe10);
+    const bool okp = fabs(__dsub_rn(xp10, np_)) < KC.tie_thr_tab, oke = fabs(__dsub_rn(xe10, ne_)) < KC.tie_thr_tab;
+    if (!(okp & oke)) {            // factors re-read from memory: rare path
+        np_ = __dmul_rn(r_round1_exact(__dmul_rn(__ldg(par + 2), Praw)), 10.0);
+        ne_ = __dmul_rn(r_round1_exact(__dmul_rn(__ldg(par + 3), Eraw)), 10.0);
+        ip = __double2int_rn(np_);
+        ie = __double2int_rn(ne_);
+    }
+    const double a2 = pow_tab_half(min(ip, nclamp), t1, t2);
+    const double b2 = pow_tab_half(min(ie, nclamp), t1, t2);
+    return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
+}
+
+template <bool F32EXP, int CTAS>
+__global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);            // NST2 * STAGE2_DBL
+    double *ptab = stage + NST2 * STAGE2_DBL;                        // SPB * PT_WARP_DBL
+    double *saved = ptab + SPB * PT_WARP_DBL;                        // 2 * SPB * 32: stores at the start of a chunk
+    uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * SPB * 32);   // NST2
+    int *left = reinterpret_cast<int *>(full + NST2);                // NST2: warps that have left the stage
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
+    const int set = sg * SPB + warp;
+    const bool set_ok = set < a.nsets;
+    const int tile0 = cs * a.tiles_per_split;
+    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
+    const int nchunk = a.ntime_pad / TM2;
+    const int total = (tile1 - tile0) * nchunk;
+
+    if (tid < NST2) left[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NST2; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;
+    if (tid == 0) {
+        for (int g = 0; g < NST2 && g < total; ++g) {
+            mbar_arrive_expect_tx(&full[g], STAGE2_DBL * 8);
+            bulk_g2s(stage + g * STAGE2_DBL, Fbase + (size_t)g * STAGE2_DBL, STAGE2_DBL * 8, &full[g]);
+        }
+    }
+
+    // one region: every lane of the warp has the set's parameters (only the area differs)
+    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4;
+    CellPar p = load_par(par, 1, 0, 0.0, a.forcing_ok);
+    // smallest n whose argument n c reaches the clamp 26 (airGR: min(P/X1, 13)); tables hold exp(min(., 26))
+    const double U26 = 0x1.2c14a02335a6fp+16;                       // 26 * 2048 / ln 2
+    const double ncd = ceil(U26 / p.g);
+    const int nclamp = ncd < 1073741824.0 ? (int)ncd : 1073741824;   // NaN parameters: results are NaN anyway
+    double *mytab = ptab + warp * PT_WARP_DBL;
+    for (int i = lane; i < PT_N; i += 32) {
+        mytab[i] = exp_idx2048_half(clamp_u26((double)(i * PT_N) * p.g), g_exp2_tab2048);            // T1h
+        mytab[PT_N + i] = 2.0 * exp_idx2048_half(clamp_u26((double)i * p.g), g_exp2_tab2048);        // T2
+    }
+    __syncwarp();
+    const uint32_t t1 = smem_u32(mytab), t2 = t1 + PT_N * 8;
+    const bool set_tab = p.thr >= 0.0 && p.X1 >= 1.0 && p.fp10 >= 0.0 && p.fe10 >= 0.0;
+
+    double *myout = a.partial + ((size_t)cs * a.nsets + (set_ok ? set : 0)) * a.ntime;
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const bool writer = set_ok && (lane & 3) == 0;
+    int g = 0, nredo = 0;
+    const int g0 = 0;
+    bool branchy = false;
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int cell = tile * 32 + lane;
+        const bool cell_ok = cell < a.ncell;
+        p.area = cell_ok ? a.area[cell] : 0.0;
+        // table mode needs 0 <= 10 f x < 65535 for every month of every lane (+inf marks negative / non-finite forcing)
+        bool lane_tab = set_tab;
+        if (cell_ok) lane_tab = lane_tab && (p.fp10 * a.frange[2 * cell] < 65535.0) && (p.fe10 * a.frange[2 * cell + 1] < 65535.0);
+        const bool use_tab = __all_sync(0xffffffffu, lane_tab);
+        double S = 0.3, R = 0.5 * p.X2 * p.iX1;                    // stores divided by X1; airGR starts at 0.3 X1, 0.5 X2
+        const double aX1 = p.area * p.X1;
+        for (int ch = 0; ch < nchunk; ++ch, ++g) {
+            const int st = g % NST2;
+            mbar_wait(&full[st], (g / NST2) & 1);
+            if (set_ok) {
+                const double *sp = stage + st * STAGE2_DBL + lane;
+                bool redo = true;
+                if (use_tab && !branchy) {
+                    // branch-free pass over the 8 months; repeated below if a lane sat on a rounding tie
+                    saved[tid] = S;
+                    saved[SPB * 32 + tid] = R;
+                    bool tie = false;
+                    double v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) v[m] = aX1 * step_tab_nb<F32EXP>(p, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp, tie);
+                    redo = __any_sync(0xffffffffu, tie);
+                    if (!redo) {
+                        double s = warp_reduce8(v, lane);
+                        const int t = ch * TM2 + ridx;
+                        if (writer && t < a.ntime) atomicAdd(myout + t, s * __ldg(a.tconv + t));
+                    } else {
+                        S = saved[tid];
+                        R = saved[SPB * 32 + tid];
+                        // parameter sets whose factors make ties common (e.g. three-decimal factors on one-decimal
+                        // forcing: one value in a thousand) go month by month for the rest of the launch
+                        nredo += 16;
+                        branchy = nredo > g - g0 + 64;
+                    }
+                }
+                if (redo) {
+                    // month by month (ties, or the general formulation); the butterfly adds in warp_reduce8's order
+#pragma unroll 1
+                    for (int m = 0; m < 8; ++m) {
+                        double q = use_tab ? step_tab<F32EXP>(p, par, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp)
+                                           : step_fast4<F32EXP>(p, sp[m * 64], sp[m * 64 + 32], S, R, g_exp2_tab2048);
+                        q = warp_sum_f64(aX1 * q);
+                        const int t = ch * TM2 + m;
+                        if (lane == 0 && t < a.ntime) atomicAdd(myout + t, q * __ldg(a.tconv + t));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // this warp's reads of the stage are complete; release / acquire on left[st] orders them before the refill
+                __threadfence_block();
+                if (atomicAdd(&left[st], 1) == SPB - 1) {
+                    __threadfence_block();
+                    left[st] = 0;
+                    const int gn = g + NST2;
+                    if (gn < total) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive_expect_tx(&full[st], STAGE2_DBL * 8);
+                        bulk_g2s(stage + st * STAGE2_DBL, Fbase + (size_t)gn * STAGE2_DBL, STAGE2_DBL * 8, &full[st]);
+                    }
+                }
+            }
+        }
+    }
+}

@@ -46,7 +46,7 @@ __device__ const double g_exp2_tab2048[2048] = {
 // (the first build spent ~60 of its ~200 instructions per month on such moves).
 struct MathK {
     double magic, nmagic, tenth, inv_ln2_32, nln2_32_hi, ln2_32_lo, c6, c5, c4, c3, two_ninths, third, tie_thr,
-        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo, inv_ln2_2048, nln2_2048, e1, e2, e3;
+        nf32_delta, inv_ln2_256, nln2_256_hi, nln2_256_lo, inv_ln2_2048, nln2_2048, e1, e2, e3, tie_thr_tab;
 };
 __constant__ MathK KC = {GR2M_MAGIC,
                          -GR2M_MAGIC,
@@ -69,7 +69,8 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          -0x1.62e42fefa39efp-12,      // -(ln2/2048) rounded to nearest
                          0x1.62e42fefa39efp-12,       // L = ln2/2048
                          0x1.ebfbdff82c58fp-25,       // L^2/2
-                         0x1.c6b08d704a0c0p-38};      // L^3/6
+                         0x1.c6b08d704a0c0p-38,       // L^3/6
+                         0.49999999};                 // tie window of the table-mode kernel (|10 f x| < 2^16), gr2m_calib3.cuh
 
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
