@@ -279,6 +279,7 @@ struct CalibArgs {
     double *partial;                           // [csplit][nsets][ntime]
     const double *frange;                      // per cell max P, max E (k_cell_range); table-mode kernel only
     int ncell, ntiles, ntime, ntime_pad, nreg, nsets, nsg, tiles_per_split, f32exp, forcing_ok;
+    int group_tiles;                           // tiles per canonical partial sum (k_gr2m_calib4)
 };
 
 // Calibration-mode recursion: every (cell, set) is simulated for all months; only the outlet sums
@@ -796,39 +797,61 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
                                b->stream));
         }
     }
-    // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
+    const bool fast = !(flags & GR2M_MATH_LITERAL);
+    // one region: per-set power tables (gr2m_calib3.cuh); several regions: a lane's X1 depends on its cell
+    static const bool no_tab = getenv("GR2M_CALIB_GENERIC") != nullptr;
+    const bool tabmode = fast && b->nreg == 1 && !no_tab;
     const int nsg = ceil_div(nsets, SPB);
-    const int target = b->sm_count * 4 * 8;
-    int csplit = ceil_div(target, nsg);
-    if (csplit > b->ntiles) csplit = b->ntiles;
-    if (csplit < 1) csplit = 1;
-    int tiles_per_split = ceil_div(b->ntiles, csplit);
-    csplit = ceil_div(b->ntiles, tiles_per_split);
+    int csplit, tiles_per_split, group_tiles = 0;
+    if (tabmode) {
+        // canonical groups of tiles (a function of the number of cells only): one partial sum per group, set and month,
+        // so a set's outlet sums do not depend on the batch it is evaluated in nor on how many ranks share the sets
+        group_tiles = 2;
+        while (group_tiles * 2 * 32 <= b->ntiles) group_tiles *= 2;
+        const int ngroups = ceil_div(b->ntiles, group_tiles);
+        int gps = (int)((long long)ngroups * nsg / ((long long)b->sm_count * 3 * 16));   // >= ~16 waves of blocks when possible
+        if (gps < 1) gps = 1;
+        tiles_per_split = gps * group_tiles;
+        csplit = ngroups;
+    } else {
+        // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
+        const int target = b->sm_count * 4 * 8;
+        csplit = ceil_div(target, nsg);
+        if (csplit > b->ntiles) csplit = b->ntiles;
+        if (csplit < 1) csplit = 1;
+        tiles_per_split = ceil_div(b->ntiles, csplit);
+        csplit = ceil_div(b->ntiles, tiles_per_split);
+    }
     if ((rc = b->partial.ensure((size_t)csplit * nsets * b->ntime * sizeof(double)))) return rc;
     if (!qt_dev) {
         if ((rc = b->qt.ensure((size_t)nsets * b->ntime * sizeof(double)))) return rc;
         qt_dev = b->qt.as<double>();
     }
-    const bool fast = !(flags & GR2M_MATH_LITERAL);
     CalibArgs a;
     a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = params_dev;
     a.tconv = fast ? b->conv.as<double>() : b->den.as<double>();
     a.region = b->region.as<int>(); a.partial = b->partial.as<double>();
     a.ncell = b->ncell; a.ntiles = b->ntiles; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad; a.nreg = b->nreg;
-    a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split;
+    a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = tiles_per_split; a.group_tiles = group_tiles;
     a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0;
     a.forcing_ok = b->forcing_ok;
     a.frange = b->frange.as<double>();
-    // one region: per-set power tables (gr2m_calib3.cuh); several regions: a lane's X1 depends on its cell
-    static const bool no_tab = getenv("GR2M_CALIB_GENERIC") != nullptr;
-    if (fast && b->nreg == 1 && !no_tab) {
-        const size_t smem = (size_t)(NST2 * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * SPB * 32) * sizeof(double) + NST2 * 12;
-        static const int ctas = getenv("GR2M_CALIB3_CTAS") ? atoi(getenv("GR2M_CALIB3_CTAS")) : 3;   // experiment switch
-        auto kern = a.f32exp ? k_gr2m_calib3<true, 3> : (ctas == 2 ? k_gr2m_calib3<false, 2> : ctas == 4 ? k_gr2m_calib3<false, 4> : k_gr2m_calib3<false, 3>);
+    if (tabmode) {
+        static const int ctas = getenv("GR2M_CALIB_CTAS") ? atoi(getenv("GR2M_CALIB_CTAS")) : 3;   // experiment switches
+        static const int cpt = getenv("GR2M_CALIB_CPT") ? atoi(getenv("GR2M_CALIB_CPT")) : 2;
+        static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 1;
+        const int c = cpt == 1 ? 1 : 2;
+        const size_t smem = (size_t)(NST2 * c * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * c * SPB * 32) * sizeof(double) + NST2 * 12;
+        void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, true>;
+        if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, true>;
+        else if (c == 1) kern = ctas == 4 ? k_gr2m_calib4<false, 4, 1, false> : k_gr2m_calib4<false, 3, 1, false>;
+        else if (ctas == 2) kern = magic ? k_gr2m_calib4<false, 2, 2, true> : k_gr2m_calib4<false, 2, 2, false>;
+        else if (!magic) kern = k_gr2m_calib4<false, 3, 2, false>;
+        const int nblk_split = ceil_div(b->ntiles, tiles_per_split);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, b->stream));
         CK(cudaMemsetAsync(b->partial.p, 0, (size_t)csplit * nsets * b->ntime * sizeof(double), b->stream));
-        kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
+        kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, b->stream));
     } else {

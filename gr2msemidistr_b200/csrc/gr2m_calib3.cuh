@@ -13,6 +13,9 @@
 // 30 KiB of per-CTA accumulators and lets the tables in.
 #pragma once
 
+#ifndef GR2M_WHATIF
+#define GR2M_WHATIF 0     /* timing experiments only (scripts/whatif.sh): drop one instruction group, results are wrong */
+#endif
 constexpr int PT_N = 256;                 // entries per table level
 constexpr int PT_WARP_DBL = 2 * PT_N;     // doubles per warp
 
@@ -58,12 +61,20 @@ __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, do
     // (b2 + 1/2) + (1 - s1)(b2 - 1/2) = b2 (2 - s1) + s1/2: one FP64 instruction less
     double s2 = div_fast3(s1, __fma_rn(b2, 2.0 - s1, 0.5 * s1));
     double c = __fma_rn(s2 * s2, s2, 1.0);
+#if GR2M_WHATIF == 1
+    double y = __fma_rn(c, -0.2, 1.0);            // no cube root: -5 FP64, -4 XU, -1 FMUL
+#else
     double y = rcbrt_fast(c);
+#endif
     if (F32EXP) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
     double sn = s2 * y;
     double d = (s - s1) + (s2 - sn);
     double rho2 = p.X2 * (__fma_rn(np_, p.cP, rho) + d);
+#if GR2M_WHATIF == 5
+    double q = rho2 * rho2 * 0.01;               // no third division: -4 FP64, -1 XU, -1 MOV
+#else
     double q = div_fast3(rho2 * rho2, rho2 + p.kappa);
+#endif
     rho = rho2 - q;
     s = sn;
     return q;
@@ -72,17 +83,35 @@ __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, do
 // Table-mode month, branch-free: the rounding decision is rint(10 f x); `tie` collects the lanes that were within
 // 1e-8 of a decimal tie (|10 f x| < 2^16 here, ulp <= 1.5e-11: R's candidate comparison cannot disagree with rint
 // outside that window).  The caller repeats the 8-month chunk with step_tab when any lane raised it.
-template <bool F32EXP>
+template <bool F32EXP, bool MAGIC>
 __device__ __forceinline__ double step_tab_nb(const CellPar &p, double Praw, double Eraw, double &s, double &rho,
                                               uint32_t t1, uint32_t t2, int nclamp, bool &tie)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
-    double np_ = rint(xp10), ne_ = rint(xe10);
-    int ip = __double2int_rn(xp10), ie = __double2int_rn(xe10);
+    double np_, ne_;
+    int ip, ie;
+    if (MAGIC) {      // rint and the integer from one magic add each (FP64 pipe) instead of FRND + F2I (XU pipe)
+        double tp = __dadd_rn(xp10, KC.magic), te = __dadd_rn(xe10, KC.magic);
+        ip = __double2loint(tp); ie = __double2loint(te);
+        np_ = __dadd_rn(tp, KC.nmagic); ne_ = __dadd_rn(te, KC.nmagic);
+    } else {
+#if GR2M_WHATIF == 3
+        np_ = xp10; ne_ = xe10; ip = __double2loint(xp10) & 0xffff; ie = __double2loint(xe10) & 0xffff;   // no conversions: -4 XU
+#else
+        np_ = rint(xp10); ne_ = rint(xe10);
+        ip = __double2int_rn(xp10); ie = __double2int_rn(xe10);
+#endif
+    }
     const bool okp = fabs(__dsub_rn(xp10, np_)) < KC.tie_thr_tab, oke = fabs(__dsub_rn(xe10, ne_)) < KC.tie_thr_tab;
     tie |= !(okp & oke);
+#if GR2M_WHATIF == 2
+    const double a2 = __fma_rn(xp10, 1e-4, 0.6), b2 = __fma_rn(xe10, 1e-4, 0.6);   // no table lookups: -4 LDS, -10 integer
+#elif GR2M_WHATIF == 4
+    const double a2 = pow_tab_half(1234, t1, t2) + xp10, b2 = pow_tab_half(77, t1, t2) + xe10;   // uniform lookups (no bank conflicts)
+#else
     const double a2 = pow_tab_half(min(ip, nclamp), t1, t2);
     const double b2 = pow_tab_half(min(ie, nclamp), t1, t2);
+#endif
     return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
 }
 
@@ -106,15 +135,15 @@ __device__ __forceinline__ double step_tab(const CellPar &p, const double *__res
     return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
 }
 
-template <bool F32EXP, int CTAS>
+template <bool F32EXP, int CTAS, int NST, bool MAGIC>
 __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);            // NST2 * STAGE2_DBL
-    double *ptab = stage + NST2 * STAGE2_DBL;                        // SPB * PT_WARP_DBL
+    double *stage = reinterpret_cast<double *>(smem_raw);            // NST * STAGE2_DBL
+    double *ptab = stage + NST * STAGE2_DBL;                        // SPB * PT_WARP_DBL
     double *saved = ptab + SPB * PT_WARP_DBL;                        // 2 * SPB * 32: stores at the start of a chunk
-    uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * SPB * 32);   // NST2
-    int *left = reinterpret_cast<int *>(full + NST2);                // NST2: warps that have left the stage
+    uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * SPB * 32);   // NST
+    int *left = reinterpret_cast<int *>(full + NST);                // NST: warps that have left the stage
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
@@ -125,15 +154,15 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
     const int nchunk = a.ntime_pad / TM2;
     const int total = (tile1 - tile0) * nchunk;
 
-    if (tid < NST2) left[tid] = 0;
+    if (tid < NST) left[tid] = 0;
     if (tid == 0) {
-        for (int i = 0; i < NST2; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
     const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;
     if (tid == 0) {
-        for (int g = 0; g < NST2 && g < total; ++g) {
+        for (int g = 0; g < NST && g < total; ++g) {
             mbar_arrive_expect_tx(&full[g], STAGE2_DBL * 8);
             bulk_g2s(stage + g * STAGE2_DBL, Fbase + (size_t)g * STAGE2_DBL, STAGE2_DBL * 8, &full[g]);
         }
@@ -172,8 +201,8 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
         double S = 0.3, R = 0.5 * p.X2 * p.iX1;                    // stores divided by X1; airGR starts at 0.3 X1, 0.5 X2
         const double aX1 = p.area * p.X1;
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
-            const int st = g % NST2;
-            mbar_wait(&full[st], (g / NST2) & 1);
+            const int st = g % NST;
+            mbar_wait(&full[st], (g / NST) & 1);
             if (set_ok) {
                 const double *sp = stage + st * STAGE2_DBL + lane;
                 bool redo = true;
@@ -184,10 +213,17 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
                     bool tie = false;
                     double v[8];
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) v[m] = aX1 * step_tab_nb<F32EXP>(p, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp, tie);
+                    for (int m = 0; m < 8; ++m) v[m] = aX1 * step_tab_nb<F32EXP, MAGIC>(p, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp, tie);
                     redo = __any_sync(0xffffffffu, tie);
+#if GR2M_WHATIF != 0
+                    redo = false;
+#endif
                     if (!redo) {
+#if GR2M_WHATIF == 6
+                        double s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));   // no cross-lane reduction
+#else
                         double s = warp_reduce8(v, lane);
+#endif
                         const int t = ch * TM2 + ridx;
                         if (writer && t < a.ntime) atomicAdd(myout + t, s * __ldg(a.tconv + t));
                     } else {
@@ -218,11 +254,174 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
                 if (atomicAdd(&left[st], 1) == SPB - 1) {
                     __threadfence_block();
                     left[st] = 0;
-                    const int gn = g + NST2;
+                    const int gn = g + NST;
                     if (gn < total) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         mbar_arrive_expect_tx(&full[st], STAGE2_DBL * 8);
                         bulk_g2s(stage + st * STAGE2_DBL, Fbase + (size_t)gn * STAGE2_DBL, STAGE2_DBL * 8, &full[st]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// k_gr2m_calib4: the same table-mode recursion with CPT cells per thread and canonical partial sums.
+//  * CPT = 2: a lane carries the stores of two cells (tiles t and t+1); the two recursions are independent, so the
+//    instruction stream of a warp holds two dependency chains to interleave and the per-chunk work (cross-lane
+//    reduction, reductions to global memory, stage hand-over) is shared by twice the units.
+//  * Outlet sums are accumulated per GROUP of a.group_tiles consecutive tiles (a function of the number of cells only,
+//    calib_group_tiles): partial[group][set][month].  The groups do not depend on how a launch is cut into blocks, so a set's sums are the same bits whatever the batch size,
+//    the number of ranks or the SM count (k_objective adds the groups in index order).
+// ---------------------------------------------------------------------------------------------------------
+
+template <bool F32EXP, int CTAS, int CPT, bool MAGIC>
+__global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
+{
+    constexpr int NST = NST2, STG = CPT * STAGE2_DBL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage = reinterpret_cast<double *>(smem_raw);            // NST * STG
+    double *ptab = stage + NST * STG;                                // SPB * PT_WARP_DBL
+    double *saved = ptab + SPB * PT_WARP_DBL;                        // 2 * CPT * SPB * 32: stores at the start of a chunk
+    uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * CPT * SPB * 32);   // NST
+    int *left = reinterpret_cast<int *>(full + NST);                 // NST: warps that have left the stage
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
+    const int set = sg * SPB + warp;
+    const bool set_ok = set < a.nsets;
+    const int tile0 = cs * a.tiles_per_split;                        // a multiple of a.group_tiles
+    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
+    const int nchunk = a.ntime_pad / TM2;
+    const int npair = (tile1 - tile0 + CPT - 1) / CPT;
+    const int total = npair * nchunk;
+
+    if (tid < NST) left[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // stage gi = 8 months (chunk gi % nchunk) of the CPT tiles of pair gi / nchunk: one 4 KiB bulk copy per tile
+    auto issue = [&](int gi) {
+        const int pi = gi / nchunk, ch = gi - pi * nchunk, st = gi % NST;
+        const int tA = tile0 + pi * CPT, nvalid = min(CPT, tile1 - tA);
+        mbar_arrive_expect_tx(&full[st], nvalid * STAGE2_DBL * 8);
+        for (int c = 0; c < nvalid; ++c)
+            bulk_g2s(stage + st * STG + c * STAGE2_DBL, a.F + ((size_t)(tA + c) * a.ntime_pad + ch * TM2) * 64, STAGE2_DBL * 8,
+                     &full[st]);
+    };
+    if (tid == 0)
+        for (int gi = 0; gi < NST && gi < total; ++gi) issue(gi);
+
+    // one region: every lane of the warp has the set's parameters (only the area differs)
+    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4;
+    CellPar p = load_par(par, 1, 0, 0.0, a.forcing_ok);
+    // smallest n whose argument n c reaches the clamp 26 (airGR: min(P/X1, 13)); tables hold exp(min(., 26))
+    const double U26 = 0x1.2c14a02335a6fp+16;                       // 26 * 2048 / ln 2
+    const double ncd = ceil(U26 / p.g);
+    const int nclamp = ncd < 1073741824.0 ? (int)ncd : 1073741824;   // NaN parameters: results are NaN anyway
+    double *mytab = ptab + warp * PT_WARP_DBL;
+    for (int i = lane; i < PT_N; i += 32) {
+        mytab[i] = exp_idx2048_half(clamp_u26((double)(i * PT_N) * p.g), g_exp2_tab2048);            // T1h
+        mytab[PT_N + i] = 2.0 * exp_idx2048_half(clamp_u26((double)i * p.g), g_exp2_tab2048);        // T2
+    }
+    __syncwarp();
+    const uint32_t t1 = smem_u32(mytab), t2 = t1 + PT_N * 8;
+    const bool set_tab = p.thr >= 0.0 && p.X1 >= 1.0 && p.fp10 >= 0.0 && p.fe10 >= 0.0;
+
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const bool writer = set_ok && (lane & 3) == 0;
+    int g = 0, nredo = 0;
+    bool branchy = false;
+    for (int pi = 0; pi < npair; ++pi) {
+        const int tA = tile0 + pi * CPT;
+        double *myout = a.partial + ((size_t)(tA / a.group_tiles) * a.nsets + (set_ok ? set : 0)) * a.ntime;
+        double aX1[CPT], S[CPT], R[CPT];
+        int soff[CPT];                  // a missing last tile re-reads the first one's forcing with area 0
+        bool lane_tab = set_tab;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const bool has = tA + c < tile1;
+            const int cell = (tA + c) * 32 + lane;
+            const bool cell_ok = has && cell < a.ncell;
+            aX1[c] = (cell_ok ? a.area[cell] : 0.0) * p.X1;
+            soff[c] = (has ? c : 0) * STAGE2_DBL + lane;
+            // table mode needs 0 <= 10 f x < 65535 for every month of every lane (+inf marks negative / non-finite forcing)
+            if (cell_ok) lane_tab = lane_tab && (p.fp10 * a.frange[2 * cell] < 65535.0) && (p.fe10 * a.frange[2 * cell + 1] < 65535.0);
+            S[c] = 0.3;                                               // stores divided by X1; airGR starts at 0.3 X1, 0.5 X2
+            R[c] = 0.5 * p.X2 * p.iX1;
+        }
+        const bool use_tab = __all_sync(0xffffffffu, lane_tab);
+        for (int ch = 0; ch < nchunk; ++ch, ++g) {
+            const int st = g % NST;
+            mbar_wait(&full[st], (g / NST) & 1);
+            if (set_ok) {
+                const double *sp = stage + st * STG;
+                bool redo = true;
+                if (use_tab && !branchy) {
+                    // branch-free pass over the 8 months; repeated below if a lane sat on a rounding tie
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        saved[(2 * c) * SPB * 32 + tid] = S[c];
+                        saved[(2 * c + 1) * SPB * 32 + tid] = R[c];
+                    }
+                    bool tie = false;
+                    double v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        v[m] = aX1[0] * step_tab_nb<F32EXP, MAGIC>(p, sp[soff[0] + m * 64], sp[soff[0] + m * 64 + 32], S[0], R[0], t1, t2, nclamp, tie);
+#pragma unroll
+                        for (int c = 1; c < CPT; ++c)
+                            v[m] = __fma_rn(aX1[c], step_tab_nb<F32EXP, MAGIC>(p, sp[soff[c] + m * 64], sp[soff[c] + m * 64 + 32], S[c], R[c], t1, t2, nclamp, tie), v[m]);
+                    }
+                    redo = __any_sync(0xffffffffu, tie);
+                    if (!redo) {
+                        double s = warp_reduce8(v, lane);
+                        const int t = ch * TM2 + ridx;
+                        if (writer && t < a.ntime) atomicAdd(myout + t, s * __ldg(a.tconv + t));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            S[c] = saved[(2 * c) * SPB * 32 + tid];
+                            R[c] = saved[(2 * c + 1) * SPB * 32 + tid];
+                        }
+                        // parameter sets whose factors make ties common (e.g. three-decimal factors on one-decimal
+                        // forcing: one value in a thousand) go month by month for the rest of the launch
+                        nredo += 16;
+                        branchy = nredo > g + 64;
+                    }
+                }
+                if (redo) {
+                    // month by month (ties, or the general formulation); the butterfly adds in warp_reduce8's order
+#pragma unroll 1
+                    for (int m = 0; m < 8; ++m) {
+                        double q = 0.0;
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
+                            const double qc = use_tab ? step_tab<F32EXP>(p, par, Pr, Er, S[c], R[c], t1, t2, nclamp)
+                                                      : step_fast4<F32EXP>(p, Pr, Er, S[c], R[c], g_exp2_tab2048);
+                            q = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, q);
+                        }
+                        q = warp_sum_f64(q);
+                        const int t = ch * TM2 + m;
+                        if (lane == 0 && t < a.ntime) atomicAdd(myout + t, q * __ldg(a.tconv + t));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // this warp's reads of the stage are complete; release / acquire on left[st] orders them before the refill
+                __threadfence_block();
+                if (atomicAdd(&left[st], 1) == SPB - 1) {
+                    __threadfence_block();
+                    left[st] = 0;
+                    if (g + NST < total) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(g + NST);
                     }
                 }
             }
