@@ -28,6 +28,7 @@ void gr2m_set_error(const char *fmt, ...);
         }                                                                                          \
     } while (0)
 
+void gr2m_count_launch(void);   // every kernel launch of the library is counted (gr2m_kernel_launches)
 int gr2m_check_device(void);   // GR2M_OK, or GR2M_ERR_NODEVICE with the error text set
 int gr2m_current_device(void);
 
@@ -38,6 +39,11 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // cudaFree of a few hundred MB costs milliseconds to tenths of a second.  `got` = the block's real size.
 int gr2m_dev_alloc(void **p, size_t bytes, size_t *got);
 void gr2m_dev_free(void *p, size_t bytes);
+
+// Copies between device memory and (possibly pageable) host memory; large pageable transfers are pipelined through a
+// ring of pinned buffers with the host-side memcpy on helper threads (gr2m.cu).
+int gr2m_copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st);
+int gr2m_copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
 
 // A handle that gives back many buffers at once synchronises the device once instead of once per buffer:
 // while a FreeBatch is alive on the calling thread, gr2m_dev_free() skips its own synchronisation.

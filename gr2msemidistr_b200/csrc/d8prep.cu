@@ -154,26 +154,26 @@ extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int
     DCK(cudaMemcpy(dz, dem, n * 8, cudaMemcpyHostToDevice));
     DCK(cudaMemcpy(dv, valid, n, cudaMemcpyHostToDevice));
     dim3 rowgrid(ceil_div(ncol, 256), nrow);
-    k_d8_init<<<rowgrid, 256>>>(dz, dv, nrow, ncol, dF, de);
+    gr2m_count_launch(), k_d8_init<<<rowgrid, 256>>>(dz, dv, nrow, ncol, dF, de);
     DCK(cudaGetLastError());
     dim3 tgrid(ceil_div(ncol, TILE), ceil_div(nrow, TILE)), tblk(TILE, TILE);
     int flag = 1;
     for (long long it = 0; flag && it < (long long)nrow + ncol + 16; ++it) {   // each pass moves >= INNER cells
         DCK(cudaMemset(dflag, 0, sizeof(int)));
-        k_d8_fill<<<tgrid, tblk>>>(dz, dv, de, nrow, ncol, dF, dflag);
+        gr2m_count_launch(), k_d8_fill<<<tgrid, tblk>>>(dz, dv, de, nrow, ncol, dF, dflag);
         DCK(cudaGetLastError());
         DCK(cudaMemcpy(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
     }
-    k_d8_descent<<<rowgrid, 256>>>(dF, dv, de, nrow, ncol, dc, dd);
+    gr2m_count_launch(), k_d8_descent<<<rowgrid, 256>>>(dF, dv, de, nrow, ncol, dc, dd);
     DCK(cudaGetLastError());
     flag = 1;
     for (int t = 1; flag && t < nrow * ncol + 2; ++t) {
         DCK(cudaMemset(dflag, 0, sizeof(int)));
-        k_d8_flat_step<<<rowgrid, 256>>>(dF, dv, nrow, ncol, t, dc, dd, dflag);
+        gr2m_count_launch(), k_d8_flat_step<<<rowgrid, 256>>>(dF, dv, nrow, ncol, t, dc, dd, dflag);
         DCK(cudaGetLastError());
         DCK(cudaMemcpy(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
     }
-    k_d8_finish<<<ceil_div((long long)n, 256), 256>>>(dv, n, dc, filled ? dF : nullptr);
+    gr2m_count_launch(), k_d8_finish<<<ceil_div((long long)n, 256), 256>>>(dv, n, dc, filled ? dF : nullptr);
     DCK(cudaGetLastError());
     DCK(cudaMemcpy(flowdir, dc, n * 2, cudaMemcpyDeviceToHost));
     if (filled) DCK(cudaMemcpy(filled, dF, n * 8, cudaMemcpyDeviceToHost));

@@ -14,6 +14,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <atomic>
+#include <future>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -36,6 +38,10 @@ void gr2m_set_error(const char *fmt, ...)
 }
 
 extern "C" const char *gr2m_last_error(void) { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void gr2m_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long gr2m_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int gr2m_version(void) { return 1; }
 
 extern "C" int gr2m_device_count(void)
@@ -154,6 +160,121 @@ extern "C" int gr2m_release_cached_memory(void)
     return GR2M_OK;
 }
 
+// ---- large copies to / from pageable host memory ---------------------------------------------------
+// R's matrices are ordinary (pageable) memory.  A plain cudaMemcpy on them is staged by the driver through one
+// buffer with one host thread (~4-10 GB/s); here the staging is explicit: a ring of pinned buffers, the device
+// copy of one chunk overlapping the host memcpy of the others on helper threads.
+namespace {
+constexpr size_t STG_CHUNK = 16u << 20;
+constexpr int STG_NBUF = 4;
+constexpr size_t STG_MIN_BYTES = 32u << 20;     // below this a plain copy is as good
+std::mutex g_stg_mu;
+void *g_stg_buf[STG_NBUF] = {nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_stg_ev[STG_NBUF];
+bool stg_init_locked()
+{
+    if (g_stg_buf[0]) return true;
+    for (int i = 0; i < STG_NBUF; ++i) {
+        if (cudaHostAlloc(&g_stg_buf[i], STG_CHUNK, cudaHostAllocPortable) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_stg_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j <= i; ++j) if (g_stg_buf[j]) { cudaFreeHost(g_stg_buf[j]); g_stg_buf[j] = nullptr; }
+            return false;
+        }
+    }
+    return true;
+}
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+}  // namespace
+
+// device -> host; returns after the data is in `dst` when staged, otherwise asynchronously on `st` like cudaMemcpyAsync
+int gr2m_copy_d2h(void *dst, const void *src_dev, size_t bytes, cudaStream_t st)
+{
+    static const bool off = getenv("GR2M_NO_STAGING") != nullptr;
+    if (bytes < STG_MIN_BYTES || off || host_is_pinned(dst)) {
+        CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        return GR2M_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_stg_mu);
+    if (!stg_init_locked()) {
+        CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        return GR2M_OK;
+    }
+    std::future<void> fut[STG_NBUF];
+    const size_t nch = (bytes + STG_CHUNK - 1) / STG_CHUNK;
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i < nch && err == cudaSuccess; ++i) {
+        const int bi = (int)(i % STG_NBUF);
+        if (fut[bi].valid()) fut[bi].get();               // the host copy out of this buffer is done
+        const size_t o = i * STG_CHUNK, n = bytes - o < STG_CHUNK ? bytes - o : STG_CHUNK;
+        err = cudaMemcpyAsync(g_stg_buf[bi], (const char *)src_dev + o, n, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaEventRecord(g_stg_ev[bi], st);
+        if (err != cudaSuccess) break;
+        void *pin = g_stg_buf[bi];
+        cudaEvent_t ev = g_stg_ev[bi];
+        char *d = (char *)dst + o;
+        fut[bi] = std::async(std::launch::async, [pin, ev, d, n]() { cudaEventSynchronize(ev); memcpy(d, pin, n); });
+    }
+    for (auto &f : fut) if (f.valid()) f.get();
+    if (err != cudaSuccess) {
+        gr2m_set_error("staged device-to-host copy failed: %s", cudaGetErrorString(err));
+        cudaGetLastError();
+        return GR2M_ERR_CUDA;
+    }
+    return GR2M_OK;
+}
+
+// host -> device; the host memory may be reused when this returns if staged, otherwise as for cudaMemcpyAsync
+int gr2m_copy_h2d(void *dst_dev, const void *src, size_t bytes, cudaStream_t st)
+{
+    static const bool off = getenv("GR2M_NO_STAGING") != nullptr;
+    if (bytes < STG_MIN_BYTES || off || host_is_pinned(src)) {
+        CK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
+        return GR2M_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_stg_mu);
+    if (!stg_init_locked()) {
+        CK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
+        return GR2M_OK;
+    }
+    const size_t nch = (bytes + STG_CHUNK - 1) / STG_CHUNK;
+    std::future<void> fut[STG_NBUF];
+    bool used[STG_NBUF] = {false, false, false, false};
+    auto fill = [&](size_t i) {     // helper thread: wait until the previous device copy out of the buffer is done, then fill it
+        const int bi = (int)(i % STG_NBUF);
+        const size_t o = i * STG_CHUNK, n = bytes - o < STG_CHUNK ? bytes - o : STG_CHUNK;
+        void *pin = g_stg_buf[bi];
+        cudaEvent_t ev = g_stg_ev[bi];
+        const bool wait = used[bi];
+        const char *sp = (const char *)src + o;
+        fut[bi] = std::async(std::launch::async, [pin, ev, sp, n, wait]() { if (wait) cudaEventSynchronize(ev); memcpy(pin, sp, n); });
+    };
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i < nch && i < (size_t)STG_NBUF - 1; ++i) fill(i);
+    for (size_t i = 0; i < nch && err == cudaSuccess; ++i) {
+        const int bi = (int)(i % STG_NBUF);
+        fut[bi].get();
+        const size_t o = i * STG_CHUNK, n = bytes - o < STG_CHUNK ? bytes - o : STG_CHUNK;
+        err = cudaMemcpyAsync((char *)dst_dev + o, g_stg_buf[bi], n, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaEventRecord(g_stg_ev[bi], st);
+        used[bi] = true;
+        if (i + STG_NBUF - 1 < nch) fill(i + STG_NBUF - 1);
+    }
+    for (auto &f : fut) if (f.valid()) f.get();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);      // the ring may be reused by the next call
+    if (err != cudaSuccess) {
+        gr2m_set_error("staged host-to-device copy failed: %s", cudaGetErrorString(err));
+        cudaGetLastError();
+        return GR2M_ERR_CUDA;
+    }
+    return GR2M_OK;
+}
+
 int gr2m_check_device(void)
 {
     if (gr2m_device_count() <= 0) {
@@ -204,22 +325,6 @@ __global__ void k_tile_forcing(const double *__restrict__ P, const double *__res
             F[base + lx] = sp[lx][j];
             F[base + 32 + lx] = se[lx][j];
         }
-    }
-}
-
-// out[c][r] = in[r][c]  (in: rows x cols with leading dimension ldin; out: cols x rows)
-__global__ void k_transpose(const double *__restrict__ in, int rows, int cols, int ldin, double *__restrict__ out)
-{
-    __shared__ double s[32][33];
-    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        int r = r0 + j, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) s[j][threadIdx.x] = in[(size_t)r * ldin + c];
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        int c = c0 + j, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) out[(size_t)c * rows + r] = s[threadIdx.x][j];
     }
 }
 
@@ -395,29 +500,34 @@ __global__ void __launch_bounds__(SPB * 32, CALIB_CTAS) k_gr2m_calib2(CalibArgs 
 struct SimArgs {
     const double *F, *area, *params, *den, *S0, *R0;
     const int *region;
-    double *out;        // [5][ntime][ncell_pad] month-major: PR, AE, SM, RU, QS
+    double *out[5];     // PR, AE, SM, RU, QS, each [ncell][ntime] = R's column-major [ntime x ncell]; NULL = not wanted
     double *S_end, *R_end;
     int ncell, ncell_pad, ntime, ntime_pad, nreg, f32exp, forcing_ok;
 };
 
-// Simulation-mode recursion: one parameter vector, every series written (Run:223-229).
+// Simulation-mode recursion: one parameter vector, every series written (Run:223-229) -- straight into R's
+// layout.  A thread owns a subbasin for all months; results of SIM_MB months are parked in a per-warp shared-memory
+// tile [series][cell][month] and written out as runs of SIM_MB consecutive months per subbasin (128-byte segments),
+// so no transposed copy of the 5 x [ntime x ncell] outputs is ever made.
+constexpr int SIM_MB = 16, SIM_WARPS = 4, SIM_LD = SIM_MB + 1;
+
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_gr2m_sim(SimArgs a)
+__global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
 {
-    __shared__ double tab[32];
+    extern __shared__ double sim_smem[];
+    double *tab = sim_smem;                                                      // 32: 2^(j/32)
+    double *tile = sim_smem + 32 + (threadIdx.x >> 5) * (5 * 32 * SIM_LD);       // [5][32][SIM_LD]
     if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     __syncthreads();
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;      // ncell_pad is a multiple of 32: whole warps leave together
     if (cell >= a.ncell_pad) return;
     const bool ok = cell < a.ncell;
-    const int tile = cell >> 5, lane = cell & 31;
+    const int tl = cell >> 5, lane = cell & 31;
     CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0, a.forcing_ok);
     double S = (a.S0 && ok) ? a.S0[cell] : 0.3 * p.X1;
     double R = (a.R0 && ok) ? a.R0[cell] : 0.5 * p.X2;
-    const double *__restrict__ f = a.F + (size_t)tile * a.ntime_pad * 64 + lane;
+    const double *__restrict__ f = a.F + (size_t)tl * a.ntime_pad * 64 + lane;
     const double *__restrict__ den = a.den;
-    double *__restrict__ out = a.out;
-    const size_t plane = (size_t)a.ntime * a.ncell_pad;
     // the recursion is one dependent chain per thread: keep the forcing of the next U months in flight so a
     // month costs its arithmetic, not a memory round trip (ntime_pad rows exist in F; den is guarded)
     constexpr int U = 4;
@@ -427,31 +537,51 @@ __global__ void __launch_bounds__(128) k_gr2m_sim(SimArgs a)
         Pn[u] = __ldg(f + (size_t)u * 64); En[u] = __ldg(f + (size_t)u * 64 + 32);
         Dn[u] = u < a.ntime ? __ldg(den + u) : 1.0;
     }
-    for (int t0 = 0; t0 < a.ntime; t0 += U) {
-        double Pc_[U], Ec_[U], Dc_[U];
+    const int cell0 = cell - lane;
+    for (int tb = 0; tb < a.ntime; tb += SIM_MB) {
+#pragma unroll 1
+        for (int t0 = tb; t0 < tb + SIM_MB && t0 < a.ntime; t0 += U) {
+            double Pc_[U], Ec_[U], Dc_[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { Pc_[u] = Pn[u]; Ec_[u] = En[u]; Dc_[u] = Dn[u]; }
+            for (int u = 0; u < U; ++u) { Pc_[u] = Pn[u]; Ec_[u] = En[u]; Dc_[u] = Dn[u]; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int tn = t0 + U + u;
-            if (tn < a.ntime) {
-                Pn[u] = __ldg(f + (size_t)tn * 64); En[u] = __ldg(f + (size_t)tn * 64 + 32); Dn[u] = __ldg(den + tn);
+            for (int u = 0; u < U; ++u) {
+                const int tn = t0 + U + u;
+                if (tn < a.ntime) {
+                    Pn[u] = __ldg(f + (size_t)tn * 64); En[u] = __ldg(f + (size_t)tn * 64 + 32); Dn[u] = __ldg(den + tn);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u;
+                if (t < a.ntime) {
+                    StepOut o = FAST ? step_fast(p, Pc_[u], Ec_[u], S, R, a.f32exp, tab)
+                                     : step_literal(p, Pc_[u], Ec_[u], S, R, a.f32exp);
+                    double *w = tile + lane * SIM_LD + (t - tb);
+                    w[0] = o.Pc;
+                    w[32 * SIM_LD] = o.AE;
+                    w[2 * 32 * SIM_LD] = S;
+                    w[3 * 32 * SIM_LD] = o.Q;
+                    w[4 * 32 * SIM_LD] = (p.area * o.Q) / Dc_[u];
+                }
             }
         }
+        __syncwarp();
+        // half a warp writes one subbasin's SIM_MB months (consecutive in R's layout); two subbasins per pass
+        const int nm = min(SIM_MB, a.ntime - tb);
+        const int mo = lane & (SIM_MB - 1), sub = lane / SIM_MB;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t0 + u;
-            if (t < a.ntime) {
-                StepOut o = FAST ? step_fast(p, Pc_[u], Ec_[u], S, R, a.f32exp, tab)
-                                 : step_literal(p, Pc_[u], Ec_[u], S, R, a.f32exp);
-                const size_t k = (size_t)t * a.ncell_pad + cell;
-                __stcs(out + k, o.Pc);
-                __stcs(out + plane + k, o.AE);
-                __stcs(out + 2 * plane + k, S);
-                __stcs(out + 3 * plane + k, o.Q);
-                __stcs(out + 4 * plane + k, (p.area * o.Q) / Dc_[u]);
+        for (int v = 0; v < 5; ++v) {
+            double *__restrict__ dst = a.out[v];
+            if (!dst) continue;
+            const double *src = tile + v * 32 * SIM_LD;
+#pragma unroll 4
+            for (int r = sub; r < 32; r += 32 / SIM_MB) {
+                const int c = cell0 + r;
+                if (c < a.ncell && mo < nm) __stcs(dst + (size_t)c * a.ntime + tb + mo, src[r * SIM_LD + mo]);
             }
         }
+        __syncwarp();
     }
     if (ok) {
         if (a.S_end) a.S_end[cell] = S;
@@ -562,6 +692,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 9: r = r_round1_cvt(x[i], fabs(x[i]) < 1e14 ? GR2M_TIE_THR : -1.0); break;
         case 10: r = exp_tab2048(x[i], g_exp2_tab2048); break;
         case 11: r = 2.0 * exp_idx2048_half(clamp_u26(x[i] * 0x1.71547652b82fep+11), g_exp2_tab2048); break;
+        case 12: r = rcbrt_fast_poly(x[i]); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;
@@ -577,7 +708,7 @@ struct gr2m_basin {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int forcing_ok = 0;   // every |P|, |E| < 1e5 and finite (checked on the device at upload)
-    DevBuf F, frange, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, sim_t, s0, r0, send, rend;
+    DevBuf F, frange, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, s0, r0, send, rend;
     double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
     int qobs_n = 0;
 };
@@ -588,7 +719,7 @@ static void basin_free(gr2m_basin *b)
     cudaSetDevice(b->device);
     FreeBatch fb;
     DevBuf *bufs[] = {&b->F, &b->frange, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
-                      &b->crit, &b->qobs, &b->sim_out, &b->sim_t, &b->s0, &b->r0, &b->send, &b->rend};
+                      &b->crit, &b->qobs, &b->sim_out, &b->s0, &b->r0, &b->send, &b->rend};
     for (DevBuf *d : bufs) d->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -642,8 +773,7 @@ static int basin_create_common(int ntime, int ncell, const double *P, const doub
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     if (!on_device) {
-        step(cudaMemcpyAsync(rawP.p, P, nraw, cudaMemcpyHostToDevice, b->stream));
-        step(cudaMemcpyAsync(rawE.p, E, nraw, cudaMemcpyHostToDevice, b->stream));
+        if (gr2m_copy_h2d(rawP.p, P, nraw, b->stream) || gr2m_copy_h2d(rawE.p, E, nraw, b->stream)) step(cudaErrorUnknown);
     }
     step(cudaMemcpyAsync(b->area.p, area, ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     step(cudaMemcpyAsync(b->region.p, region_id, ncell * sizeof(int), cudaMemcpyHostToDevice, b->stream));
@@ -653,9 +783,9 @@ static int basin_create_common(int ntime, int ncell, const double *P, const doub
         dim3 grid(b->ntiles, ceil_div(b->ntime_pad, 32)), blk(32, 8);
         int *bad = reinterpret_cast<int *>(b->conv.as<char>() + (size_t)ntime * sizeof(double));
         step(cudaMemsetAsync(bad, 0, sizeof(int), b->stream));
-        k_tile_forcing<<<grid, blk, 0, b->stream>>>(Pd, Ed, ncell, ntime, b->ntime_pad, b->F.as<double>(), bad);
+        gr2m_count_launch(), k_tile_forcing<<<grid, blk, 0, b->stream>>>(Pd, Ed, ncell, ntime, b->ntime_pad, b->F.as<double>(), bad);
         step(cudaGetLastError());
-        k_cell_range<<<ceil_div(ncell, 128), 128, 0, b->stream>>>(b->F.as<double>(), ncell, ntime, b->ntime_pad,
+        gr2m_count_launch(), k_cell_range<<<ceil_div(ncell, 128), 128, 0, b->stream>>>(b->F.as<double>(), ncell, ntime, b->ntime_pad,
                                                                   b->frange.as<double>());
         step(cudaGetLastError());
         int hbad = 1;
@@ -719,11 +849,13 @@ extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, c
     REQUIRE(b && params, "NULL handle or params");
     REQUIRE((S0 == nullptr) == (R0 == nullptr), "S0 and R0 must both be given or both be NULL");
     CK(cudaSetDevice(b->device));
-    const size_t plane = (size_t)b->ntime * b->ncell_pad;
+    const size_t plane = (size_t)b->ntime * b->ncell;
+    double *outs[5] = {PR, AE, SM, RU, QS};
+    int nout = 0, slot[5];
+    for (int v = 0; v < 5; ++v) slot[v] = outs[v] ? nout++ : -1;
     int rc;
     if ((rc = b->params.ensure(4 * b->nreg * sizeof(double)))) return rc;
-    if ((rc = b->sim_out.ensure(5 * plane * sizeof(double)))) return rc;
-    if ((rc = b->sim_t.ensure((size_t)b->ncell * b->ntime * sizeof(double)))) return rc;
+    if (nout && (rc = b->sim_out.ensure(nout * plane * sizeof(double)))) return rc;
     if ((rc = b->send.ensure(b->ncell * sizeof(double)))) return rc;
     if ((rc = b->rend.ensure(b->ncell * sizeof(double)))) return rc;
     CK(cudaMemcpyAsync(b->params.p, params, 4 * b->nreg * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -736,27 +868,22 @@ extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, c
     SimArgs a;
     a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = b->params.as<double>();
     a.den = b->den.as<double>(); a.S0 = S0 ? b->s0.as<double>() : nullptr; a.R0 = R0 ? b->r0.as<double>() : nullptr;
-    a.region = b->region.as<int>(); a.out = b->sim_out.as<double>();
+    a.region = b->region.as<int>();
+    for (int v = 0; v < 5; ++v) a.out[v] = outs[v] ? b->sim_out.as<double>() + slot[v] * plane : nullptr;
     a.S_end = b->send.as<double>(); a.R_end = b->rend.as<double>();
     a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad;
     a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
+    const size_t smem = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * sizeof(double);
+    auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, b->stream));
-    int grid = ceil_div(b->ncell_pad, 128);
-    if (flags & GR2M_MATH_LITERAL) k_gr2m_sim<false><<<grid, 128, 0, b->stream>>>(a);
-    else k_gr2m_sim<true><<<grid, 128, 0, b->stream>>>(a);
+    gr2m_count_launch(), kern<<<ceil_div(b->ncell_pad, SIM_WARPS * 32), SIM_WARPS * 32, smem, b->stream>>>(a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->ev1, b->stream));
     b->timed = true;
-    double *outs[5] = {PR, AE, SM, RU, QS};
-    for (int v = 0; v < 5; ++v) {
-        if (!outs[v]) continue;
-        dim3 g(ceil_div(b->ncell, 32), ceil_div(b->ntime, 32)), blk(32, 8);
-        k_transpose<<<g, blk, 0, b->stream>>>(b->sim_out.as<double>() + v * plane, b->ntime, b->ncell, b->ncell_pad,
-                                              b->sim_t.as<double>());
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(outs[v], b->sim_t.p, (size_t)b->ncell * b->ntime * sizeof(double), cudaMemcpyDeviceToHost,
-                           b->stream));
-    }
+    // the series are already in the caller's layout: straight (staged when large and pageable) copies
+    for (int v = 0; v < 5; ++v)
+        if (outs[v] && (rc = gr2m_copy_d2h(outs[v], a.out[v], plane * sizeof(double), b->stream))) return rc;
     if (S_end) CK(cudaMemcpyAsync(S_end, b->send.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     if (R_end) CK(cudaMemcpyAsync(R_end, b->rend.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -806,7 +933,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     if (tabmode) {
         // canonical groups of tiles (a function of the number of cells only): one partial sum per group, set and month,
         // so a set's outlet sums do not depend on the batch it is evaluated in nor on how many ranks share the sets
-        group_tiles = 2;
+        group_tiles = 4;                 // a multiple of the cells per thread of every k_gr2m_calib4 variant
         while (group_tiles * 2 * 32 <= b->ntiles) group_tiles *= 2;
         const int ngroups = ceil_div(b->ntiles, group_tiles);
         int gps = (int)((long long)ngroups * nsg / ((long long)b->sm_count * 3 * 16));   // >= ~16 waves of blocks when possible
@@ -839,19 +966,20 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     if (tabmode) {
         static const int ctas = getenv("GR2M_CALIB_CTAS") ? atoi(getenv("GR2M_CALIB_CTAS")) : 3;   // experiment switches
         static const int cpt = getenv("GR2M_CALIB_CPT") ? atoi(getenv("GR2M_CALIB_CPT")) : 2;
-        static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 1;
-        const int c = cpt == 1 ? 1 : 2;
+        static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 0;
+        const int c = cpt == 1 ? 1 : cpt == 4 ? 4 : 2;
         const size_t smem = (size_t)(NST2 * c * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * c * SPB * 32) * sizeof(double) + NST2 * 12;
-        void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, true>;
-        if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, true>;
+        void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, false>;
+        if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, false>;
         else if (c == 1) kern = ctas == 4 ? k_gr2m_calib4<false, 4, 1, false> : k_gr2m_calib4<false, 3, 1, false>;
+        else if (c == 4) kern = k_gr2m_calib4<false, 2, 4, false>;
         else if (ctas == 2) kern = magic ? k_gr2m_calib4<false, 2, 2, true> : k_gr2m_calib4<false, 2, 2, false>;
-        else if (!magic) kern = k_gr2m_calib4<false, 3, 2, false>;
+        else if (magic) kern = k_gr2m_calib4<false, 3, 2, true>;
         const int nblk_split = ceil_div(b->ntiles, tiles_per_split);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, b->stream));
         CK(cudaMemsetAsync(b->partial.p, 0, (size_t)csplit * nsets * b->ntime * sizeof(double), b->stream));
-        kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
+        gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, b->stream));
     } else {
@@ -861,7 +989,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
                          : (a.f32exp ? k_gr2m_calib2<false, true> : k_gr2m_calib2<false, false>);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, b->stream));
-        kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
+        gr2m_count_launch(), kern<<<nsg * csplit, SPB * 32, smem, b->stream>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, b->stream));
     }
@@ -870,7 +998,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     o.qt = qt_dev; o.of = of_dev; o.crit = crit_dev;
     o.csplit = csplit; o.nsets = nsets; o.ntime = b->ntime; o.warmup = warmup < 0 ? 0 : warmup; o.which = which;
     o.single_cell = b->ncell == 1; o.unrounded = (flags & GR2M_SINK_UNROUNDED) ? 1 : 0; o.has_obs = has_obs;
-    k_objective<<<ceil_div((long long)nsets * 32, 128), 128, 0, b->stream>>>(o);
+    gr2m_count_launch(), k_objective<<<ceil_div((long long)nsets * 32, 128), 128, 0, b->stream>>>(o);
     CK(cudaGetLastError());
     b->timed = true;
     return GR2M_OK;
@@ -1006,10 +1134,10 @@ extern "C" int gr2m_fp64_peak_mix(int mode, int iters, double *tinstr)
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(e0));
-        if (mode == 0) k_fp64_peak_mix<0><<<blocks, 256>>>(iters, 1.0, sink);
-        if (mode == 1) k_fp64_peak_mix<1><<<blocks, 256>>>(iters, 1.0, sink);
-        if (mode == 2) k_fp64_peak_mix<2><<<blocks, 256>>>(iters, 1.0, sink);
-        if (mode == 3) k_fp64_peak_mix<3><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 0) gr2m_count_launch(), k_fp64_peak_mix<0><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 1) gr2m_count_launch(), k_fp64_peak_mix<1><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 2) gr2m_count_launch(), k_fp64_peak_mix<2><<<blocks, 256>>>(iters, 1.0, sink);
+        if (mode == 3) gr2m_count_launch(), k_fp64_peak_mix<3><<<blocks, 256>>>(iters, 1.0, sink);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1037,11 +1165,11 @@ extern "C" int gr2m_fp64_peak_rrr(int iters, double *tflops)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    k_fp64_peak_rrr<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);
+    gr2m_count_launch(), k_fp64_peak_rrr<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaEventRecord(e0));
-        k_fp64_peak_rrr<<<blocks, 256>>>(iters, 1.0, sink);
+        gr2m_count_launch(), k_fp64_peak_rrr<<<blocks, 256>>>(iters, 1.0, sink);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1068,11 +1196,11 @@ extern "C" int gr2m_fp64_peak(int iters, double *tflops, float *ms_out)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    k_fp64_peak<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);   // warm-up
+    gr2m_count_launch(), k_fp64_peak<<<blocks, 256>>>(iters / 4 + 1, 1.0, sink);   // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaEventRecord(e0));
-        k_fp64_peak<<<blocks, 256>>>(iters, 1.0, sink);
+        gr2m_count_launch(), k_fp64_peak<<<blocks, 256>>>(iters, 1.0, sink);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1100,7 +1228,7 @@ extern "C" int gr2m_debug_math(int op, int n, const double *x, const double *y, 
     CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
     if (y) CK(cudaMemcpy(dy, y, n * sizeof(double), cudaMemcpyHostToDevice));
     else CK(cudaMemset(dy, 0, n * sizeof(double)));
-    k_debug_math<<<ceil_div(n, 256), 256>>>(op, n, dx, dy, dout);
+    gr2m_count_launch(), k_debug_math<<<ceil_div(n, 256), 256>>>(op, n, dx, dy, dout);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dout);

@@ -63,8 +63,10 @@ __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, do
     double c = __fma_rn(s2 * s2, s2, 1.0);
 #if GR2M_WHATIF == 1
     double y = __fma_rn(c, -0.2, 1.0);            // no cube root: -5 FP64, -4 XU, -1 FMUL
+#elif GR2M_WHATIF == 7
+    double y = rcbrt_fast(c);                    // XU-pipe seed (F2F, LG2, EX2, F2F)
 #else
-    double y = rcbrt_fast(c);
+    double y = rcbrt_fast_poly(c);               // c = 1 + s2^3 in [1, 2]
 #endif
     if (F32EXP) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
     double sn = s2 * y;

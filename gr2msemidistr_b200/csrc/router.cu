@@ -284,8 +284,8 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
     TRC(act.ensure(actbytes));
     TCK(cudaMemsetAsync(srcmap.p, 0xff, (size_t)n * 4, st));
     TCK(cudaMemsetAsync(act.p, 0, actbytes, st));
-    k_rt_srcmap<<<nbs, 256, 0, st>>>(src.as<int32_t>(), nsub, level, srcmap.as<int32_t>());
-    k_rt_mark<<<nbs, 256, 0, st>>>(src.as<int32_t>(), nsub, level, receiver, act.as<unsigned>());
+    gr2m_count_launch(), k_rt_srcmap<<<nbs, 256, 0, st>>>(src.as<int32_t>(), nsub, level, srcmap.as<int32_t>());
+    gr2m_count_launch(), k_rt_mark<<<nbs, 256, 0, st>>>(src.as<int32_t>(), nsub, level, receiver, act.as<unsigned>());
     TCK(cudaGetLastError());
     TRC(acells.ensure(std::max<size_t>(4, (size_t)n * 4)));
     TRC(nsel.ensure(16));
@@ -304,7 +304,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
         const int nba = ceil_div(nact, 256);
         TRC(isnode.ensure((size_t)nact * 4));
         TRC(rank.ensure((size_t)nact * 4));
-        k_rt_classify<<<nba, 256, 0, st>>>(acells.as<int32_t>(), nact, p->ncol, p->inmask.as<uint8_t>(), act.as<unsigned>(),
+        gr2m_count_launch(), k_rt_classify<<<nba, 256, 0, st>>>(acells.as<int32_t>(), nact, p->ncol, p->inmask.as<uint8_t>(), act.as<unsigned>(),
                                            srcmap.as<int32_t>(), isnode.as<int32_t>());
         TCK(cudaGetLastError());
         TCK(cub::DeviceScan::InclusiveSum(nullptr, tb, isnode.as<int32_t>(), rank.as<int32_t>(), nact, st));
@@ -323,7 +323,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
     if (nn > 0) {
         const int nba = ceil_div(nact, 256), nbn = ceil_div(nn, 256);
         TRC(node_cell.ensure((size_t)nn * 4));
-        k_rt_nodes<<<nba, 256, 0, st>>>(acells.as<int32_t>(), nact, isnode.as<int32_t>(), rank.as<int32_t>(),
+        gr2m_count_launch(), k_rt_nodes<<<nba, 256, 0, st>>>(acells.as<int32_t>(), nact, isnode.as<int32_t>(), rank.as<int32_t>(),
                                         srcmap.as<int32_t>(), node_cell.as<int32_t>(), r->node_src.as<int32_t>());
         // 3. segments: srcmap becomes seg (cell -> nearest node at or above it)
         int32_t *seg = srcmap.as<int32_t>();
@@ -333,19 +333,19 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
         TRC(ckey2.ensure((size_t)nn * 8));
         TRC(cval.ensure((size_t)nn * 4));
         TRC(ccnt.ensure(((size_t)nn + 1) * 4));
-        k_rt_seg_init<<<nbn, 256, 0, st>>>(node_cell.as<int32_t>(), nn, seg);
-        k_rt_seg_walk<<<nbn, 256, 0, st>>>(node_cell.as<int32_t>(), nn, p->ncol, level, receiver, seg, parent.as<int32_t>(),
+        gr2m_count_launch(), k_rt_seg_init<<<nbn, 256, 0, st>>>(node_cell.as<int32_t>(), nn, seg);
+        gr2m_count_launch(), k_rt_seg_walk<<<nbn, 256, 0, st>>>(node_cell.as<int32_t>(), nn, p->ncol, level, receiver, seg, parent.as<int32_t>(),
                                            ckey.as<unsigned long long>());
         TCK(cudaGetLastError());
         // 4. children in (parent, k slot) order
-        k_rt_iota<<<nbn, 256, 0, st>>>(cval.as<int32_t>(), nn);
+        gr2m_count_launch(), k_rt_iota<<<nbn, 256, 0, st>>>(cval.as<int32_t>(), nn);
         TCK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ckey.as<unsigned long long>(), ckey2.as<unsigned long long>(),
                                             cval.as<int32_t>(), r->child_idx.as<int32_t>(), nn, 0, 64, st));
         if (tb > temp.cap) TRC(temp.ensure(tb));
         TCK(cub::DeviceRadixSort::SortPairs(temp.p, tb, ckey.as<unsigned long long>(), ckey2.as<unsigned long long>(),
                                             cval.as<int32_t>(), r->child_idx.as<int32_t>(), nn, 0, 64, st));
         TCK(cudaMemsetAsync(ccnt.p, 0, ((size_t)nn + 1) * 4, st));
-        k_rt_child_count<<<nbn, 256, 0, st>>>(parent.as<int32_t>(), nn, ccnt.as<int32_t>());
+        gr2m_count_launch(), k_rt_child_count<<<nbn, 256, 0, st>>>(parent.as<int32_t>(), nn, ccnt.as<int32_t>());
         TCK(cudaGetLastError());
         TCK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ccnt.as<int32_t>(), r->child_off.as<int32_t>(), nn + 1, st));
         if (tb > temp.cap) TRC(temp.ensure(tb));
@@ -358,13 +358,13 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
         while (changed) {
             TCK(cudaMemsetAsync(nsel.p, 0, 4, st));
             for (int it = 0; it < 16; ++it)
-                k_rt_height_step<<<nbn, 256, 0, st>>>(parent.as<int32_t>(), nn, height.as<int32_t>(), nsel.as<int>());
+                gr2m_count_launch(), k_rt_height_step<<<nbn, 256, 0, st>>>(parent.as<int32_t>(), nn, height.as<int32_t>(), nsel.as<int>());
             TCK(cudaGetLastError());
             TCK(cudaMemcpyAsync(&changed, nsel.p, 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
         }
         TRC(hkey2.ensure((size_t)nn * 4));
-        k_rt_iota<<<nbn, 256, 0, st>>>(cval.as<int32_t>(), nn);
+        gr2m_count_launch(), k_rt_iota<<<nbn, 256, 0, st>>>(cval.as<int32_t>(), nn);
         TCK(cub::DeviceRadixSort::SortPairs(nullptr, tb, height.as<int32_t>(), hkey2.as<int32_t>(), cval.as<int32_t>(),
                                             r->horder.as<int32_t>(), nn, 0, 32, st));
         if (tb > temp.cap) TRC(temp.ensure(tb));
@@ -376,7 +376,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
         r->nh = hmax + 1;
         TRC(hist.ensure(((size_t)r->nh) * 4));
         TCK(cudaMemsetAsync(hist.p, 0, (size_t)r->nh * 4, st));
-        k_rt_height_hist<<<nbn, 256, 0, st>>>(height.as<int32_t>(), nn, hist.as<int32_t>());
+        gr2m_count_launch(), k_rt_height_hist<<<nbn, 256, 0, st>>>(height.as<int32_t>(), nn, hist.as<int32_t>());
         TCK(cudaGetLastError());
         std::vector<int32_t> hh(r->nh);
         TCK(cudaMemcpyAsync(hh.data(), hist.p, (size_t)r->nh * 4, cudaMemcpyDeviceToHost, st));
@@ -395,7 +395,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
         TRC(key.ensure((size_t)npc * 8));
         TRC(flag.ensure((size_t)npc));
         TRC(ksel.ensure((size_t)npc * 8));
-        k_rt_cand<<<ceil_div(npc, 256), 256, 0, st>>>(poff.as<int32_t>(), nsub, pcells.as<int32_t>(), npc, level,
+        gr2m_count_launch(), k_rt_cand<<<ceil_div(npc, 256), 256, 0, st>>>(poff.as<int32_t>(), nsub, pcells.as<int32_t>(), npc, level,
                                                       p->contam.as<uint8_t>(), use_contam, act.as<unsigned>(),
                                                       srcmap.as<int32_t>(), key.as<unsigned long long>(),
                                                       flag.as<uint8_t>(), r->haszero.as<int32_t>());
@@ -427,7 +427,7 @@ static int router_build(wfa_router *r, const int32_t *src_host, const int32_t *p
     }
     r->ncand = ncand;
     TRC(r->cand_idx.ensure(std::max<size_t>(4, (size_t)ncand * 4)));
-    k_rt_cand_off<<<ceil_div(std::max(ncand, nsub + 1), 256), 256, 0, st>>>(kuniq.as<unsigned long long>(), ncand, nsub,
+    gr2m_count_launch(), k_rt_cand_off<<<ceil_div(std::max(ncand, nsub + 1), 256), 256, 0, st>>>(kuniq.as<unsigned long long>(), ncand, nsub,
                                                                           r->cand_off.as<int32_t>(),
                                                                           r->cand_idx.as<int32_t>());
     TCK(cudaGetLastError());
@@ -500,14 +500,14 @@ static int router_apply_t(wfa_router *r, int ncols, const double *QS_dev, double
             const int v0 = r->h_hoff[h], v1 = r->h_hoff[h + 1];
             for (int b = v0; b < v1; b += 65535) {
                 dim3 grid(bx, std::min(65535, v1 - b));
-                k_rt_eval<T><<<grid, 128, 0, st>>>(r->horder.as<int32_t>(), b, v1, r->node_src.as<int32_t>(),
+                gr2m_count_launch(), k_rt_eval<T><<<grid, 128, 0, st>>>(r->horder.as<int32_t>(), b, v1, r->node_src.as<int32_t>(),
                                                    r->child_off.as<int32_t>(), r->child_idx.as<int32_t>(), QS_dev, ncols,
                                                    c0, nc, val, chunk);
             }
         }
         for (int b = 0; b < r->nsub; b += 65535) {
             dim3 grid(bx, std::min(65535, r->nsub - b));
-            k_rt_polymax<T><<<grid, 128, 0, st>>>(r->cand_off.as<int32_t>() + b, r->cand_idx.as<int32_t>(),
+            gr2m_count_launch(), k_rt_polymax<T><<<grid, 128, 0, st>>>(r->cand_off.as<int32_t>() + b, r->cand_idx.as<int32_t>(),
                                                   r->haszero.as<int32_t>() + b, r->nsub - b, val, chunk, c0, nc,
                                                   QR_dev + (size_t)b * ncols, ncols);
         }

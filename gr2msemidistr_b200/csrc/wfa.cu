@@ -1188,13 +1188,13 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PRC(f1.ensure(n * 4));
     PRC(state.ensure(4 * sizeof(int)));
     cudaStream_t st = p->stream;
-    k_topology<<<nb, 256, 0, st>>>(dir_dev, p->nrow, p->ncol, p->receiver.as<int32_t>(), p->inmask.as<uint8_t>(),
+    gr2m_count_launch(), k_topology<<<nb, 256, 0, st>>>(dir_dev, p->nrow, p->ncol, p->receiver.as<int32_t>(), p->inmask.as<uint8_t>(),
                                    p->indeg.as<int32_t>(), cnt.as<int32_t>(), p->contam.as<uint8_t>(),
                                    p->level.as<int32_t>());
     PCK(cudaGetLastError());
     int *d_state = state.as<int>();   // [0] level [1] size [2] which [3] scratch counter
     PCK(cudaMemsetAsync(d_state, 0, 4 * sizeof(int), st));
-    k_frontier_init<<<nb, 256, 0, st>>>(cnt.as<int32_t>(), n, f0.as<int32_t>(), d_state + 1);
+    gr2m_count_launch(), k_frontier_init<<<nb, 256, 0, st>>>(cnt.as<int32_t>(), n, f0.as<int32_t>(), d_state + 1);
     PCK(cudaGetLastError());
     int h[4] = {0, 0, 0, 0};
     PCK(cudaMemcpyAsync(h, d_state, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1205,7 +1205,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
             reached += h[1];
             int32_t *cur = h[2] ? f1.as<int32_t>() : f0.as<int32_t>(), *nxt = h[2] ? f0.as<int32_t>() : f1.as<int32_t>();
             PCK(cudaMemsetAsync(d_state + 3, 0, sizeof(int), st));
-            k_peel<<<ceil_div(h[1], 256), 256, 0, st>>>(cur, h[1], h[0], p->ncol, p->receiver.as<int32_t>(),
+            gr2m_count_launch(), k_peel<<<ceil_div(h[1], 256), 256, 0, st>>>(cur, h[1], h[0], p->ncol, p->receiver.as<int32_t>(),
                                                          p->inmask.as<uint8_t>(), cnt.as<int32_t>(),
                                                          p->contam.as<uint8_t>(), p->level.as<int32_t>(), nxt, d_state + 3);
             PCK(cudaGetLastError());
@@ -1215,7 +1215,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
             h[0] += 1; h[1] = nn; h[2] ^= 1;
         } else {
             PCK(cudaMemcpyAsync(d_state, h, 3 * sizeof(int), cudaMemcpyHostToDevice, st));
-            k_peel_thin<<<1, 1024, 0, st>>>(f0.as<int32_t>(), f1.as<int32_t>(), d_state, THIN_LIMIT, p->ncol,
+            gr2m_count_launch(), k_peel_thin<<<1, 1024, 0, st>>>(f0.as<int32_t>(), f1.as<int32_t>(), d_state, THIN_LIMIT, p->ncol,
                                             p->receiver.as<int32_t>(), p->inmask.as<uint8_t>(), cnt.as<int32_t>(),
                                             p->contam.as<uint8_t>(), p->level.as<int32_t>());
             PCK(cudaGetLastError());
@@ -1238,7 +1238,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PRC(p->order.ensure(n * 4));
     PRC(p->omask.ensure(n));
     PRC(p->level_off.ensure(((size_t)p->nlevels + 2) * 4));
-    k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>(),
+    gr2m_count_launch(), k_sort_keys<<<nb, 256, 0, st>>>(p->level.as<int32_t>(), n, p->nlevels, keys.as<uint32_t>(), vals.as<int32_t>(),
                                     p->contam.as<uint8_t>());
     PCK(cudaGetLastError());
     int bits = 1;
@@ -1250,7 +1250,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     PCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
                                         p->order.as<int32_t>(), n, 0, bits, st));
     PCK(cudaMemsetAsync(p->level_off.p, 0, ((size_t)p->nlevels + 2) * 4, st));
-    k_level_offsets<<<nb, 256, 0, st>>>(keys2.as<uint32_t>(), n, p->nlevels, p->level_off.as<int32_t>(),
+    gr2m_count_launch(), k_level_offsets<<<nb, 256, 0, st>>>(keys2.as<uint32_t>(), n, p->nlevels, p->level_off.as<int32_t>(),
                                         p->order.as<int32_t>(), p->inmask.as<uint8_t>(), p->omask.as<uint8_t>());
     PCK(cudaGetLastError());
     p->h_level_off.assign((size_t)p->nlevels + 1, 0);
@@ -1273,7 +1273,7 @@ static int plan_build(wfa_plan *p, const int16_t *dir_dev)
     CK(cudaMemsetAsync(p->tailmask.p, 0, n, st));
     int tb = tl < p->nlevels ? p->h_level_off[tl] : p->norder, te = p->norder;
     if (te > tb) {
-        k_tailmask<<<ceil_div(te - tb, 256), 256, 0, st>>>(p->order.as<int32_t>(), tb, te, p->ncol, tl,
+        gr2m_count_launch(), k_tailmask<<<ceil_div(te - tb, 256), 256, 0, st>>>(p->order.as<int32_t>(), tb, te, p->ncol, tl,
                                                            p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
                                                            p->tailmask.as<uint8_t>());
         CK(cudaGetLastError());
@@ -1317,11 +1317,11 @@ static int plan_build_components(wfa_plan *p)
     QRC(p->cmask.ensure(nu));
     QRC(p->cnext.ensure((size_t)nu * 4));
     const int32_t *order = p->order.as<int32_t>();
-    k_root_init<<<nb, 256, 0, st>>>(order, ub, nu, p->receiver.as<int32_t>(), root.as<int32_t>());
+    gr2m_count_launch(), k_root_init<<<nb, 256, 0, st>>>(order, ub, nu, p->receiver.as<int32_t>(), root.as<int32_t>());
     int depth = p->nlevels - lc + 1, jumps = 1;
     while ((1 << jumps) < depth) ++jumps;
-    for (int it = 0; it < jumps + 1; ++it) k_root_jump<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>());
-    k_root_keys<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>(), keys.as<uint32_t>(), vals.as<int32_t>());
+    for (int it = 0; it < jumps + 1; ++it) gr2m_count_launch(), k_root_jump<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>());
+    gr2m_count_launch(), k_root_keys<<<nb, 256, 0, st>>>(order, ub, nu, root.as<int32_t>(), keys.as<uint32_t>(), vals.as<int32_t>());
     QCK(cudaGetLastError());
     int bits = 1;
     while ((1ll << bits) < n) ++bits;
@@ -1332,16 +1332,16 @@ static int plan_build_components(wfa_plan *p)
     QCK(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, keys.as<uint32_t>(), keys2.as<uint32_t>(), vals.as<int32_t>(),
                                         p->corder.as<int32_t>(), nu, 0, bits, st));
     QCK(cudaMemsetAsync(cnt.p, 0, sizeof(int), st));
-    k_comp_flags<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), keys2.as<uint32_t>(), nu, p->level.as<int32_t>(),
+    gr2m_count_launch(), k_comp_flags<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), keys2.as<uint32_t>(), nu, p->level.as<int32_t>(),
                                      p->inmask.as<uint8_t>(), p->cmask.as<uint8_t>(), lstart.as<uint8_t>(),
                                      cbeg.as<int32_t>(), cnt.as<int>());
-    k_comp_next<<<nb, 256, 0, st>>>(lstart.as<uint8_t>(), nu, p->cnext.as<int32_t>());
+    gr2m_count_launch(), k_comp_next<<<nb, 256, 0, st>>>(lstart.as<uint8_t>(), nu, p->cnext.as<int32_t>());
     QCK(cudaGetLastError());
     int ncomp = 0;
     QCK(cudaMemcpyAsync(&ncomp, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     // CSR of upstream cells: counts -> exclusive scan -> fill
     QRC(p->cup_off.ensure(((size_t)nu + 1) * 4));
-    k_comp_upcount<<<nb, 256, 0, st>>>(p->cmask.as<uint8_t>(), nu, keys.as<int32_t>());
+    gr2m_count_launch(), k_comp_upcount<<<nb, 256, 0, st>>>(p->cmask.as<uint8_t>(), nu, keys.as<int32_t>());
     QCK(cudaMemsetAsync(p->cup_off.p, 0, 4, st));
     {
         size_t sbytes = 0;
@@ -1353,7 +1353,7 @@ static int plan_build_components(wfa_plan *p)
     QCK(cudaMemcpyAsync(&nedges, p->cup_off.as<int32_t>() + nu, sizeof(int), cudaMemcpyDeviceToHost, st));
     QCK(cudaStreamSynchronize(st));
     QRC(p->cup_idx.ensure(std::max<size_t>(16, (size_t)nedges * 4)));
-    k_comp_upfill<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(), nu, p->ncol,
+    gr2m_count_launch(), k_comp_upfill<<<nb, 256, 0, st>>>(p->corder.as<int32_t>(), p->cmask.as<uint8_t>(), nu, p->ncol,
                                       p->level.as<int32_t>(), p->cup_off.as<int32_t>(), p->cup_idx.as<uint32_t>());
     QCK(cudaGetLastError());
     QCK(cudaStreamSynchronize(st));
@@ -1414,16 +1414,16 @@ static int plan_build_runs(wfa_plan *p)
     RRC(d1.ensure((size_t)nu * 4));
     RRC(rl.ensure((size_t)nu * 4));
     RRC(flag.ensure(sizeof(int)));
-    k_run_upos<<<nb, 256, 0, st>>>(uorder, nu, upos.as<int32_t>());
-    k_run_pred<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
+    gr2m_count_launch(), k_run_upos<<<nb, 256, 0, st>>>(uorder, nu, upos.as<int32_t>());
+    gr2m_count_launch(), k_run_pred<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
                                    upos.as<int32_t>(), pred.as<int32_t>(), npu.as<uint8_t>());
-    k_run_rank_init<<<nb, 256, 0, st>>>(pred.as<int32_t>(), nu, h0.as<int32_t>(), d0.as<int32_t>());
+    gr2m_count_launch(), k_run_rank_init<<<nb, 256, 0, st>>>(pred.as<int32_t>(), nu, h0.as<int32_t>(), d0.as<int32_t>());
     RCK(cudaGetLastError());
     int32_t *hs = h0.as<int32_t>(), *hd = h1.as<int32_t>(), *ds = d0.as<int32_t>(), *dd = d1.as<int32_t>();
     int changed = 1;
     for (int it = 0; changed && it < 40; ++it) {
         RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
-        k_run_rank_step<<<nb, 256, 0, st>>>(hs, ds, nu, hd, dd, flag.as<int>());
+        gr2m_count_launch(), k_run_rank_step<<<nb, 256, 0, st>>>(hs, ds, nu, hd, dd, flag.as<int>());
         RCK(cudaGetLastError());
         RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         RCK(cudaStreamSynchronize(st));
@@ -1436,7 +1436,7 @@ static int plan_build_runs(wfa_plan *p)
     int nrl_iter = 0;
     for (; changed && nrl_iter < 100000; ++nrl_iter) {
         RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
-        k_run_level_step<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
+        gr2m_count_launch(), k_run_level_step<<<nb, 256, 0, st>>>(uorder, nu, p->ncol, lc, p->inmask.as<uint8_t>(), p->level.as<int32_t>(),
                                              upos.as<int32_t>(), hs, npu.as<uint8_t>(), rl.as<int32_t>(), flag.as<int>());
         RCK(cudaGetLastError());
         RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1449,7 +1449,7 @@ static int plan_build_runs(wfa_plan *p)
     RRC(vals.ensure((size_t)nu * 4));
     RRC(sj.ensure((size_t)nu * 4));
     RCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
-    k_run_keys<<<nb, 256, 0, st>>>(hs, ds, rl.as<int32_t>(), nu, keys.as<unsigned long long>(), vals.as<int32_t>(),
+    gr2m_count_launch(), k_run_keys<<<nb, 256, 0, st>>>(hs, ds, rl.as<int32_t>(), nu, keys.as<unsigned long long>(), vals.as<int32_t>(),
                                    flag.as<int>());
     RCK(cudaGetLastError());
     RCK(cudaMemcpyAsync(&changed, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1466,7 +1466,7 @@ static int plan_build_runs(wfa_plan *p)
     RRC(isstart.ensure((size_t)nu * 4));
     RRC(rank.ensure((size_t)nu * 4));
     RRC(cnt.ensure((size_t)nu * 4));
-    k_run_gather<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, uorder, ds, p->inmask.as<uint8_t>(), p->rcell.as<int32_t>(),
+    gr2m_count_launch(), k_run_gather<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, uorder, ds, p->inmask.as<uint8_t>(), p->rcell.as<int32_t>(),
                                      isstart.as<int32_t>(), cnt.as<int32_t>());
     RCK(cudaGetLastError());
     size_t sbytes = 0;
@@ -1485,13 +1485,13 @@ static int plan_build_runs(wfa_plan *p)
     RRC(p->rup_idx.ensure(std::max<size_t>(16, (size_t)nedges * 4)));
     RRC(p->run_start.ensure(((size_t)nr + 1) * 4));
     RRC(runrl.ensure((size_t)nr * 4));
-    k_run_starts<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), rank.as<int32_t>(), nu, p->run_start.as<int32_t>());
+    gr2m_count_launch(), k_run_starts<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), rank.as<int32_t>(), nu, p->run_start.as<int32_t>());
     RCK(cudaMemcpyAsync(p->run_start.as<int32_t>() + nr, &nu, 4, cudaMemcpyHostToDevice, st));
-    k_run_upfill<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, p->ncol, p->rcell.as<int32_t>(), p->inmask.as<uint8_t>(),
+    gr2m_count_launch(), k_run_upfill<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, p->ncol, p->rcell.as<int32_t>(), p->inmask.as<uint8_t>(),
                                      pred.as<int32_t>(), uorder, p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>());
     // the reach stream: rows per cell, their offsets, and which cell completes at which row
     RRC(p->row_off.ensure(((size_t)nu + 1) * 4));
-    k_run_rows<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(), nu,
+    gr2m_count_launch(), k_run_rows<<<nb, 256, 0, st>>>(isstart.as<int32_t>(), p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(), nu,
                                    cnt.as<int32_t>());
     RCK(cudaGetLastError());
     RCK(cub::DeviceScan::InclusiveSum(nullptr, sbytes, cnt.as<int32_t>(), p->row_off.as<int32_t>() + 1, nu, st));
@@ -1503,18 +1503,18 @@ static int plan_build_runs(wfa_plan *p)
     RCK(cudaStreamSynchronize(st));
     RRC(p->rowcell.ensure(((size_t)nrows + 2 * RS_ROWS) * 4));        // the sweep copies whole RS_ROWS blocks
     RCK(cudaMemsetAsync(p->rowcell.p, 0xff, ((size_t)nrows + 2 * RS_ROWS) * 4, st));
-    k_run_rowcell<<<nb, 256, 0, st>>>(p->row_off.as<int32_t>(), p->rcell.as<int32_t>(), nu, p->rowcell.as<int32_t>());
+    gr2m_count_launch(), k_run_rowcell<<<nb, 256, 0, st>>>(p->row_off.as<int32_t>(), p->rcell.as<int32_t>(), nu, p->rowcell.as<int32_t>());
     RRC(p->rinfo.ensure((size_t)nr * RINFO_VEC * 16));
     RRC(p->rdone.ensure((size_t)nr * 4));
     RCK(cudaMemsetAsync(p->rdone.p, 0, (size_t)nr * 4, st));
     int32_t *inv = vals.as<int32_t>();            // the sort's input values are no longer needed
-    k_run_inv<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, inv);
-    k_run_pack<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, p->rcell.as<int32_t>(),
+    gr2m_count_launch(), k_run_inv<<<nb, 256, 0, st>>>(sj.as<int32_t>(), nu, inv);
+    gr2m_count_launch(), k_run_pack<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, p->rcell.as<int32_t>(),
                                                  p->rup_off.as<int32_t>(), p->rup_idx.as<uint32_t>(),
                                                  p->row_off.as<int32_t>(), p->level.as<int32_t>(), lc,
                                                  upos.as<int32_t>(), inv, rank.as<int32_t>(), p->rinfo.as<int4>());
     p->nrows = nrows;
-    k_run_levels<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, sj.as<int32_t>(), rl.as<int32_t>(),
+    gr2m_count_launch(), k_run_levels<<<ceil_div(nr, 256), 256, 0, st>>>(p->run_start.as<int32_t>(), nr, sj.as<int32_t>(), rl.as<int32_t>(),
                                                    runrl.as<int32_t>());
     RCK(cudaGetLastError());
     std::vector<int32_t> hrl(nr);
@@ -1725,19 +1725,19 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
     CK(cudaEventRecord(p->evm, st));
     if (l0 < p->nlevels) {
         if (by_reach) {
-            k_reach_gather<T, G><<<ceil_div(nu, gpb), 256, 0, st>>>(p->rcell.as<int32_t>(), p->rup_off.as<int32_t>(),
+            gr2m_count_launch(), k_reach_gather<T, G><<<ceil_div(nu, gpb), 256, 0, st>>>(p->rcell.as<int32_t>(), p->rup_off.as<int32_t>(),
                                                                     p->rup_idx.as<uint32_t>(), p->row_off.as<int32_t>(), nu,
                                                                     A, S, ld, lds, nmonth);
             if (flags & WFA_NO_OVERLAP) {         // one launch per reach level
                 for (size_t l = 0; l + 1 < p->h_rlv_off.size(); ++l) {
                     const int r0 = p->h_rlv_off[l], r1 = p->h_rlv_off[l + 1];
-                    k_reach_sweep<T><<<ceil_div(r1 - r0, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
+                    gr2m_count_launch(), k_reach_sweep<T><<<ceil_div(r1 - r0, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
                         p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), r0, r1, S, lds, A, ld, nmonth, nullptr, nullptr, 0u);
                 }
             } else {                              // all levels in one launch, heads wait for the reaches that feed them
                 p->epoch += 1;
                 CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
-                k_reach_sweep<T><<<ceil_div(p->nruns, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
+                gr2m_count_launch(), k_reach_sweep<T><<<ceil_div(p->nruns, RS_WARPS), 32 * RS_WARPS, 0, st>>>(
                     p->rinfo.as<int4>(), p->rowcell.as<int32_t>(), 0, p->nruns, S, lds, A, ld, nmonth, p->ticket.as<int>(),
                     p->rdone.as<unsigned>(), p->epoch);
             }
@@ -1745,17 +1745,17 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
             int blocks = std::min(p->ncomp, 148 * 7);
             if (G >= 16 && nmonth <= G && !(flags & WFA_NO_FORWARD))
-                k_accum_components_fw<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
+                gr2m_count_launch(), k_accum_components_fw<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
                                                                     p->cup_idx.as<uint32_t>(), p->cnext.as<int32_t>(),
                                                                     p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(),
                                                                     A, ld, nmonth);
             else
-                k_accum_components<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
+                gr2m_count_launch(), k_accum_components<T, G><<<blocks, 288, 0, st>>>(p->corder.as<int32_t>(), p->cup_off.as<int32_t>(),
                                                                  p->cup_idx.as<uint32_t>(), p->cnext.as<int32_t>(),
                                                                  p->comps.as<int2>(), p->ncomp, p->ticket.as<int>(), A,
                                                                  ld, nmonth);
         } else if (!dataflow) {
-            k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
+            gr2m_count_launch(), k_accum_thin<T, G><<<1, 1024, 0, st>>>(order, p->level_off.as<int32_t>(), l0, p->nlevels, p->ncol, omask, A,
                                                    ld, nmonth);
         } else {
             int b = off[l0], e = p->norder;
@@ -1763,7 +1763,7 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
             CK(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
             int groups = ceil_div(e - b, 4);
             int blocks = std::min(ceil_div(groups, gpb), 148 * 4);
-            k_accum_dataflow<T, G><<<blocks, 256, 0, st>>>(order, b, e, p->ncol, omask, p->tailmask.as<uint8_t>(), A, ld,
+            gr2m_count_launch(), k_accum_dataflow<T, G><<<blocks, 256, 0, st>>>(order, b, e, p->ncol, omask, p->tailmask.as<uint8_t>(), A, ld,
                                                            nmonth, p->done.as<unsigned>(), p->epoch, p->ticket.as<int>());
         }
         CK(cudaGetLastError());
@@ -1802,10 +1802,10 @@ extern "C" int wfa_mask_dev(wfa_plan *p, int nmonth, int ld, void *WA_dev, int f
     const int use_contam = (flags & WFA_NO_CONTAMINATION) ? 0 : 1;
     long long total = p->ncell * nmonth;
     if (flags & WFA_F32)
-        k_mask<float><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
+        gr2m_count_launch(), k_mask<float><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
                                                                   use_contam, p->ncell, (float *)WA_dev, ld, nmonth);
     else
-        k_mask<double><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
+        gr2m_count_launch(), k_mask<double><<<ceil_div(total, 256), 256, 0, p->stream>>>(p->level.as<int32_t>(), p->contam.as<uint8_t>(),
                                                                    use_contam, p->ncell, (double *)WA_dev, ld, nmonth);
     CK(cudaGetLastError());
     return GR2M_OK;
@@ -1825,13 +1825,13 @@ extern "C" int wfa_accumulate(wfa_plan *p, int nmonth, const double *W, int flag
     cudaStream_t st = p->stream;
     CK(cudaMemcpyAsync(p->work.p, W, (size_t)n * nmonth * 8, cudaMemcpyHostToDevice, st));
     dim3 grid(ceil_div(n, 32), ceil_div(ld, 32)), blk(32, 8);
-    if (flags & WFA_F32) k_planes_to_cells<float><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<float>());
-    else k_planes_to_cells<double><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<double>());
+    if (flags & WFA_F32) gr2m_count_launch(), k_planes_to_cells<float><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<float>());
+    else gr2m_count_launch(), k_planes_to_cells<double><<<grid, blk, 0, st>>>(p->work.as<double>(), n, nmonth, ld, p->work2.as<double>());
     CK(cudaGetLastError());
     if ((rc = wfa_accumulate_dev(p, nmonth, ld, p->work2.p, flags))) return rc;
     if ((rc = wfa_mask_dev(p, nmonth, ld, p->work2.p, flags))) return rc;
-    if (flags & WFA_F32) k_cells_to_planes<float><<<grid, blk, 0, st>>>(p->work2.as<float>(), n, nmonth, ld, p->work.as<double>());
-    else k_cells_to_planes<double><<<grid, blk, 0, st>>>(p->work2.as<double>(), n, nmonth, ld, p->work.as<double>());
+    if (flags & WFA_F32) gr2m_count_launch(), k_cells_to_planes<float><<<grid, blk, 0, st>>>(p->work2.as<float>(), n, nmonth, ld, p->work.as<double>());
+    else gr2m_count_launch(), k_cells_to_planes<double><<<grid, blk, 0, st>>>(p->work2.as<double>(), n, nmonth, ld, p->work.as<double>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(A, p->work.p, (size_t)n * nmonth * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1898,19 +1898,19 @@ extern "C" int wfa_route(wfa_plan *p, int ntime, int nsub, const double *QS, con
         dim3 pg(nsub, ceil_div(nt, 32));
         CK(cudaMemsetAsync(p->work2.p, 0, (size_t)n * ld * esz, st));
         if (flags & WFA_F32) {
-            k_scatter<float><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
+            gr2m_count_launch(), k_scatter<float><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
                                                  p->work2.as<float>(), ld);
             CK(cudaGetLastError());
             if ((rc = wfa_accumulate_dev(p, nt, ld, p->work2.p, flags))) return rc;
-            k_polygon_max<float><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+            gr2m_count_launch(), k_polygon_max<float><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
                                                      p->contam.as<uint8_t>(), use_contam, p->work2.as<float>(), ld, ntime,
                                                      t0, nt, p->qr.as<double>());
         } else {
-            k_scatter<double><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
+            gr2m_count_launch(), k_scatter<double><<<nb, 256, 0, st>>>(p->qs.as<double>(), p->src.as<int32_t>(), nsub, ntime, t0, nt,
                                                   p->work2.as<double>(), ld);
             CK(cudaGetLastError());
             if ((rc = wfa_accumulate_dev(p, nt, ld, p->work2.p, flags))) return rc;
-            k_polygon_max<double><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
+            gr2m_count_launch(), k_polygon_max<double><<<pg, 256, 0, st>>>(p->poff.as<int32_t>(), p->pcells.as<int32_t>(), p->level.as<int32_t>(),
                                                       p->contam.as<uint8_t>(), use_contam, p->work2.as<double>(), ld,
                                                       ntime, t0, nt, p->qr.as<double>());
         }

@@ -74,7 +74,8 @@ int  gr2m_device_count(void);                    /* number of CUDA devices, 0 if
 /* Handles keep up to 8 GB of freed device blocks (up to 4 GB each) for the next handle, because the
  * reference's workflow creates and destroys one per call; this gives them back to the driver. */
 int  gr2m_release_cached_memory(void);
-int  gr2m_set_device(int device);                /* device used by subsequently created handles */
+int  gr2m_set_device(int device);                /* device used by handles the calling thread creates from now on */
+long long gr2m_kernel_launches(void);            /* kernels this library has launched since it was loaded (all devices) */
 
 /* Measured FP64 pipe peak of the current device in TFLOP/s (independent DFMA chains, 2 flop each,
  * `iters` x 64 DFMA per thread): the roofline denominator bench.py reports the recursion against. */

@@ -60,8 +60,10 @@ def test_device_math_building_blocks(capi, oracle, rng):
     big = np.array([26.0, 27.0, 1e3, 7.6e5])                  # clamped like min(WS, 13): exp(26) up to 2.2e-5
     assert np.max(np.abs(capi.debug_math(11, big) / np.exp(26.0) - 1)) < 3e-5
     assert np.array_equal(capi.debug_math(9, x), want)                             # rint by the conversion unit
-    c = rng.uniform(1, 2, 200000)
+    c = np.concatenate([rng.uniform(1, 2, 200000), [1.0, 2.0, np.nextafter(1.0, 2), np.nextafter(2.0, 1)], 1 + rng.uniform(0, 1, 20000) ** 3])
     assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 7e-16
+    assert np.max(np.abs(capi.debug_math(12, c) * np.cbrt(c) - 1)) < 7e-16         # seed without the XU pipe (c in [1, 2])
+    assert np.isnan(capi.debug_math(12, np.array([np.nan])))[0]
 
 
 @pytest.mark.parametrize("flags", [0, 16, 1, 17])
