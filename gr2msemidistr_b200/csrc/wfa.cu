@@ -1718,6 +1718,7 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
         for (int l = 1; l < l0; ++l) {
             int b = off[l], e = off[l + 1];
             cfg.gridDim = dim3(ceil_div(ceil_div(e - b, 2), gpb));
+            gr2m_count_launch();
             CK(cudaLaunchKernelEx(&cfg, k_accum_level<T, G>, order, b, e, p->ncol, omask, A, ld, nmonth));
         }
     }
@@ -1774,7 +1775,8 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
 template <typename T>
 static int sweep(wfa_plan *p, int nmonth, int ld, T *A, int flags)
 {
-    if (nmonth >= 32) return sweep_g<T, 32>(p, nmonth, ld, A, flags);
+    static const int gmin = getenv("WFA_G32_FROM") ? atoi(getenv("WFA_G32_FROM")) : 32;   // experiment: months from which 32 lanes own a cell
+    if (nmonth >= gmin) return sweep_g<T, 32>(p, nmonth, ld, A, flags);
     if (nmonth >= 16) return sweep_g<T, 16>(p, nmonth, ld, A, flags);
     if (nmonth >= 8) return sweep_g<T, 8>(p, nmonth, ld, A, flags);
     return sweep_g<T, 4>(p, nmonth, ld, A, flags);

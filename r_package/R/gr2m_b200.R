@@ -126,6 +126,57 @@ Routing_GR2MSemiDistr <- function(Model, Subbasins, Dem, AcumIni = NULL, AcumEnd
   Ans
 }
 
+# Create_Forcing_Inputs (R/Create_Forcing_Inputs.R:42): areal-mean P / PE table in airGR layout.  Host-side and once
+# per study, so it stays in R on raster + exactextractr like the reference; differences: the whole brick goes through
+# exact_extract in one call (no PSOCK cluster per variable, Create:101-108, 149-157, the first of which is never
+# stopped), and the default Members = NULL works (the reference's `if (Members == 1 | is.null(Members))`, Create:82,
+# is an error for NULL).  Same crop (extent * Buffer), same nearest-neighbour resample to `Resolution`, same
+# round(, 1) / round(Q, 3), same column names.
+.gr2m_areal_mean <- function(brick, roi, ind, Buffer, Resolution, Update) {
+  x <- if (Update) brick[[raster::nlayers(brick)]] else brick[[ind]]
+  buf <- raster::crop(x, raster::extent(roi) * Buffer)
+  fine <- raster::raster(raster::extent(buf)); raster::crs(fine) <- raster::crs(buf); raster::res(fine) <- Resolution
+  m <- exactextractr::exact_extract(raster::resample(buf, fine, method = "ngb"), sf::st_as_sf(roi), fun = "mean",
+                                    progress = FALSE)
+  round(t(as.matrix(m)), 1)                      # layers x subbasins
+}
+
+Create_Forcing_Inputs <- function(Subbasins, Precip, PotEvap, Qobs = NULL, DateIni, DateEnd,
+                                  IniGrids = "01/1981", Save = FALSE, Update = FALSE, Resolution = 0.01,
+                                  Buffer = 1.1, Members = NULL) {
+  tictoc::tic()
+  comid <- as.vector(Subbasins$COMID)
+  first <- function(x) as.Date(paste0("01/", x), "%d/%m/%Y")
+  index <- function(brick) {
+    d <- seq(first(IniGrids), by = "month", length.out = raster::nlayers(brick))
+    if (is.null(Members) || Members == 1) seq(which(d == first(DateIni)), which(d == first(DateEnd)))
+    else seq_len(raster::nlayers(brick))
+  }
+  cols <- list()
+  if (!is.null(Precip)) {
+    message("Calculating monthly mean-areal precipitation [mm]")
+    pr <- .gr2m_areal_mean(Precip, Subbasins, index(Precip), Buffer, Resolution, Update)
+    colnames(pr) <- paste0("P_", comid); cols <- c(cols, list(pr))
+  }
+  if (!is.null(PotEvap)) {
+    message("Calculating monthly mean-areal pot. evapotranspiration [mm]")
+    pe <- .gr2m_areal_mean(PotEvap, Subbasins, index(PotEvap), Buffer, Resolution, Update)
+    colnames(pe) <- paste0("E_", comid); cols <- c(cols, list(pe))
+  }
+  DatesMonths <- if (Update) first(DateEnd) else {
+    d <- seq(first(DateIni), first(DateEnd), by = "month")
+    if (is.null(Members)) d else rep(d, times = Members)
+  }
+  Ans <- data.frame(DatesR = DatesMonths, do.call(cbind, cols), check.names = FALSE)
+  if (!is.null(Qobs)) Ans$Q <- round(Qobs[, 2], 3)
+  if (Save) {
+    dir.create("./Inputs", showWarnings = FALSE)
+    utils::write.table(Ans, file = "./Inputs/Inputs_model.txt", sep = "\t", col.names = TRUE, row.names = FALSE)
+  }
+  message("Done!"); tictoc::toc()
+  Ans
+}
+
 .gr2m_save <- function(Ans, keys, RunEnd, Update) {
   dir.create("./Outputs", recursive = TRUE, showWarnings = FALSE)
   for (k in keys) {

@@ -1,18 +1,1 @@
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python - <<'PY'
-import time, numpy as np
-from gr2msemidistr_b200 import capi, synth
-capi.set_device(0)
-P,E,area,nd=synth.forcing(100000,480)
-reg=np.zeros(100000,np.int32)
-par=np.array(synth.SET0)
-for rep in range(3):
-    t0=time.perf_counter()
-    with capi.Basin(P,E,area,nd,reg,1) as b:
-        t1=time.perf_counter()
-        out=b.run(par)
-        t2=time.perf_counter()
-        k=b.last_kernel_ms()
-    print('create %.3f s  run %.3f s  kernel %.3f ms  run e2e %.3g cell-months/s'%(t1-t0,t2-t1,k,4.8e7/(t2-t1)))
-PY
+python -m pytest tests/test_r_shim.py -m gpu -q -x 2>&1 | grep -v "^$" | tail -40
