@@ -23,7 +23,7 @@ OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_release_cached_memory", "gr2m_set_device", "gr2m_kernel_launches", "gr2m_fp64_peak",
+    "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_release_cached_memory", "gr2m_set_device", "gr2m_kernel_launches", "gr2m_guard_checked", "gr2m_guard_violations", "gr2m_fp64_peak",
     "gr2m_basin_create", "gr2m_basin_create_dev", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
@@ -81,6 +81,13 @@ def _i32(a):
 
 def device_count() -> int:
     return lib().gr2m_device_count()
+
+
+def guard_counts():
+    """(buffers checked, buffers with a damaged guard band) in GR2M_GUARD=1 mode."""
+    a, b = lib().gr2m_guard_checked, lib().gr2m_guard_violations
+    a.restype = b.restype = C.c_longlong
+    return int(a()), int(b())
 
 
 def kernel_launches() -> int:

@@ -137,20 +137,17 @@ extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int
     if (rc) return rc;
     CK(cudaSetDevice(gr2m_current_device()));
     const size_t n = (size_t)nrow * ncol;
-    double *dz = nullptr, *dF = nullptr;
-    uint8_t *dv = nullptr, *de = nullptr;
-    int16_t *dc = nullptr;
-    int32_t *dd = nullptr;
-    int *dflag = nullptr;
-    auto release = [&]() { cudaFree(dz); cudaFree(dF); cudaFree(dv); cudaFree(de); cudaFree(dc); cudaFree(dd); cudaFree(dflag); };
+    DevBuf bz, bF, bv, be, bc, bd, bflag;       // through the handle allocator: block cache, guard-band debug mode
+    auto release = [&]() { FreeBatch fb; for (DevBuf *b : {&bz, &bF, &bv, &be, &bc, &bd, &bflag}) b->release(); };
 #define DCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); release(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
-    DCK(cudaMalloc(&dz, n * 8));
-    DCK(cudaMalloc(&dF, n * 8));
-    DCK(cudaMalloc(&dv, n));
-    DCK(cudaMalloc(&de, n));
-    DCK(cudaMalloc(&dc, n * 2));
-    DCK(cudaMalloc(&dd, n * 4));
-    DCK(cudaMalloc(&dflag, sizeof(int)));
+#define DRC(call) do { int r_ = (call); if (r_) { release(); return r_; } } while (0)
+    DRC(bz.ensure(n * 8)); DRC(bF.ensure(n * 8)); DRC(bv.ensure(n)); DRC(be.ensure(n)); DRC(bc.ensure(n * 2));
+    DRC(bd.ensure(n * 4)); DRC(bflag.ensure(sizeof(int)));
+    double *dz = bz.as<double>(), *dF = bF.as<double>();
+    uint8_t *dv = bv.as<uint8_t>(), *de = be.as<uint8_t>();
+    int16_t *dc = bc.as<int16_t>();
+    int32_t *dd = bd.as<int32_t>();
+    int *dflag = bflag.as<int>();
     DCK(cudaMemcpy(dz, dem, n * 8, cudaMemcpyHostToDevice));
     DCK(cudaMemcpy(dv, valid, n, cudaMemcpyHostToDevice));
     dim3 rowgrid(ceil_div(ncol, 256), nrow);
@@ -178,6 +175,7 @@ extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int
     DCK(cudaMemcpy(flowdir, dc, n * 2, cudaMemcpyDeviceToHost));
     if (filled) DCK(cudaMemcpy(filled, dF, n * 8, cudaMemcpyDeviceToHost));
 #undef DCK
+#undef DRC
     release();
     return GR2M_OK;
 }

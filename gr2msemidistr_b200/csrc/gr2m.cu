@@ -87,11 +87,48 @@ void cache_trim_locked(int dev)     // dev < 0: every device
 }
 }  // namespace
 
+// ---- guard-band debug mode (GR2M_GUARD=1) --------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this library is developed on.  As a stand-in for its memcheck
+// and initcheck, every handle buffer is allocated with GUARD_BYTES of a known pattern on either side and its payload
+// filled with 0xFF (NaN doubles, -1 integers); the bands are checked when the buffer is given back.  An out-of-bounds
+// write of any kernel shows up in gr2m_guard_violations(), a read of uninitialised memory as NaN / garbage in the
+// parity tests (tests/test_gpu_guard.py runs every kernel family once in this mode).
+namespace {
+constexpr size_t GUARD_BYTES = 512;
+constexpr unsigned char GUARD_PATTERN = 0xA5;
+std::atomic<long long> g_guard_violations{0}, g_guard_checked{0};
+bool guard_enabled()
+{
+    static const bool on = getenv("GR2M_GUARD") != nullptr && atoi(getenv("GR2M_GUARD")) != 0;
+    return on;
+}
+}  // namespace
+
+extern "C" long long gr2m_guard_violations(void) { return g_guard_violations.load(); }
+extern "C" long long gr2m_guard_checked(void) { return g_guard_checked.load(); }
+
 int gr2m_dev_alloc(void **p, size_t bytes, size_t *got)
 {
     *p = nullptr; *got = 0;
     int dev = 0;
     cudaGetDevice(&dev);
+    if (guard_enabled()) {
+        unsigned char *raw = nullptr;
+        const size_t pay = (bytes + 15) & ~(size_t)15;
+        cudaError_t e = cudaMalloc(&raw, pay + 2 * GUARD_BYTES);
+        if (e == cudaSuccess) e = cudaMemset(raw, GUARD_PATTERN, GUARD_BYTES);
+        if (e == cudaSuccess) e = cudaMemset(raw + GUARD_BYTES, 0xFF, pay);
+        if (e == cudaSuccess) e = cudaMemset(raw + GUARD_BYTES + pay, GUARD_PATTERN, GUARD_BYTES);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the fills run on the null stream, handles work on non-blocking ones
+        if (e != cudaSuccess) {
+            gr2m_set_error("guarded cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA;
+        }
+        *p = raw + GUARD_BYTES;
+        *got = bytes;          // exact capacity: the first byte past the request is already guard (after 16-byte rounding)
+        return GR2M_OK;
+    }
     if (bytes >= CACHE_MIN_BLOCK && cache_enabled()) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         int best = -1;
@@ -131,6 +168,22 @@ int gr2m_dev_alloc(void **p, size_t bytes, size_t *got)
 void gr2m_dev_free(void *p, size_t bytes)
 {
     if (!p) return;
+    if (guard_enabled()) {
+        const size_t pay = (bytes + 15) & ~(size_t)15;
+        unsigned char *raw = (unsigned char *)p - GUARD_BYTES, host[2 * GUARD_BYTES];
+        cudaDeviceSynchronize();
+        bool ok = cudaMemcpy(host, raw, GUARD_BYTES, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                  cudaMemcpy(host + GUARD_BYTES, raw + GUARD_BYTES + pay, GUARD_BYTES, cudaMemcpyDeviceToHost) == cudaSuccess;
+        for (size_t i = 0; ok && i < 2 * GUARD_BYTES; ++i) ok = host[i] == GUARD_PATTERN;
+        g_guard_checked.fetch_add(1);
+        if (!ok) {
+            g_guard_violations.fetch_add(1);
+            fprintf(stderr, "[gr2m guard] guard band of a %zu-byte device buffer was overwritten (or could not be read)\n", bytes);
+            cudaGetLastError();
+        }
+        cudaFree(raw);
+        return;
+    }
     static const bool dbg = getenv("GR2M_CACHE_DEBUG") != nullptr;
     if (dbg) fprintf(stderr, "[gr2m cache] free %zu bytes, cached %zu bytes in %zu blocks\n", bytes, g_cache_bytes, g_cache.size());
     if (bytes >= CACHE_MIN_BLOCK && bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
@@ -1211,6 +1264,23 @@ extern "C" int gr2m_fp64_peak(int iters, double *tflops, float *ms_out)
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     *tflops = 2.0 * 64.0 * (double)iters * 256.0 * blocks / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    return GR2M_OK;
+}
+
+// test hook (declared in tests only): fill an n-double handle buffer, writing `extra` doubles past its end
+__global__ void k_debug_fill(double *p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 1.0; }
+extern "C" int gr2m_debug_overrun(int n, int extra)
+{
+    REQUIRE(n > 0 && extra >= 0, "bad arguments");
+    int rc = gr2m_check_device();
+    if (rc) return rc;
+    CK(cudaSetDevice(g_device));
+    DevBuf b;
+    if ((rc = b.ensure((size_t)n * sizeof(double)))) return rc;
+    gr2m_count_launch(), k_debug_fill<<<ceil_div(n + extra, 256), 256>>>(b.as<double>(), n + extra);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    b.release();
     return GR2M_OK;
 }
 

@@ -75,6 +75,10 @@ int  gr2m_device_count(void);                    /* number of CUDA devices, 0 if
  * reference's workflow creates and destroys one per call; this gives them back to the driver. */
 int  gr2m_release_cached_memory(void);
 int  gr2m_set_device(int device);                /* device used by handles the calling thread creates from now on */
+/* GR2M_GUARD=1 in the environment: every handle buffer gets guard bands that are checked when it is released and
+ * an 0xFF-filled payload (debug stand-in for a memory checker); these count the buffers checked / found damaged. */
+long long gr2m_guard_checked(void);
+long long gr2m_guard_violations(void);
 long long gr2m_kernel_launches(void);            /* kernels this library has launched since it was loaded (all devices) */
 
 /* Measured FP64 pipe peak of the current device in TFLOP/s (independent DFMA chains, 2 flop each,
