@@ -38,22 +38,22 @@ if ROOT not in sys.path:
 METRIC = "gr2m_cell_months_per_sec"
 UNIT = "cell-months/s"
 FLOP_PER_UNIT_ALGO = 67          # nominal FP64 operations per (cell, set, month)
-try:   # FP64-pipe instructions per unit of the shipped recursion kernel, counted by ncu (profiles/)
-    _cnt = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_instr.json")))
-    FP64_INSTR_PER_UNIT, ALL_INSTR_PER_UNIT = _cnt["fp64_pipe_inst_per_unit"], _cnt["all_thread_inst_per_unit"]
+# ncu counters of the shipped recursion kernel (profiles/r2_calib_counters.json, written by scripts/ncu_summary.py from
+# the capture named inside): instructions per unit, FP64-pipe utilisation, DRAM bytes per unit
+try:
+    NCU = json.load(open(os.path.join(ROOT, "profiles", "r2_calib_counters.json")))
 except Exception:
-    FP64_INSTR_PER_UNIT, ALL_INSTR_PER_UNIT = 62.2, 116.6
+    NCU = None
 
 
-def dispatch_model(units, kernel_ms, clocks, sms=148):
-    """Dispatch cycles per warp and unit the instruction counts need (2 per FP64, 1 per other instruction)
-    against the cycles the kernel took per warp-unit and SM sub-partition."""
+def pipe_model(units, kernel_ms, clocks, sms=148):
+    """Cycles per warp and unit on one SM sub-partition against what the FP64 pipe alone needs (a warp-wide FP64
+    instruction occupies the 16-lane pipe for 2 cycles)."""
     try:
         mhz = float(clocks["sm_mhz"]) if clocks and clocks.get("sm_mhz") else 1965.0
-        need = 2.0 * FP64_INSTR_PER_UNIT + (ALL_INSTR_PER_UNIT - FP64_INSTR_PER_UNIT)
         took = kernel_ms * 1e-3 * mhz * 1e6 * sms * 4 / (units / 32.0)
-        return {"cycles_needed_per_warp_unit": need, "cycles_taken_per_warp_unit": took, "frac": need / took,
-                "all_instr_per_unit": ALL_INSTR_PER_UNIT}
+        need = 2.0 * NCU["fp64_pipe_inst_per_unit"]
+        return {"cycles_taken_per_warp_unit": took, "fp64_pipe_cycles_needed": need, "fp64_pipe_busy_live": need / took}
     except Exception as ex:
         return {"error": repr(ex)}
 
@@ -270,13 +270,22 @@ def bench_routing(a, capi, torch, rank, world, dist):
     if os.path.exists(peaks_file):
         hbm, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     gbs = units / world * 16.0 / (ms * 1e-3) / 1e9
+    # DRAM bytes per 32-month pass from the ncu launch list of the same grid (profiles/r1_wide_levels_traffic.txt): the wide
+    # levels move 190.4 GB = 14.9 B per grid cell and month; scaled to this pass's cells x months
+    traffic = 190.4e9 / (4.0e8 * 32) * float(ncell) * my_months if n == 20000 else None
     out = {"metric": "routed_cell_months_per_sec", "value": units / (ms * 1e-3), "unit": UNIT,
            "workload": f"C5 WFA: {n} x {n} synthetic D8 grid x {months_total} months, dense FP64 weights, "
                        f"{ld}-month batches, months sharded over {world} GPU(s)",
            "ms_per_pass": ms, "levels": plan.nlevels, "cells_in_order": plan.norder,
            "plan_build_s": t_plan, "grid_gen_s": t_gen,
+           "value_incl_plan_build": units / (ms * 1e-3 + t_plan),
+           "value_incl_plan_build_note": "the D8 plan (levels, reaches, stream offsets) is built once per geometry and reused "
+                                         "by every sweep; this figure charges it to this one pass over the months",
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                        "traffic": None, "algorithmic_bytes_per_unit": 16, "peak_source": hbm_src,
+                        "traffic": traffic, "algorithmic_bytes_per_unit": 16, "peak_source": hbm_src,
+                        "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum summed over the level launches of this "
+                                       "rank's months (ncu, levels 1-120 = 96 % of the non-source cells), not per launch: a "
+                                       "sweep is ~600 launches of one kernel",
                         "traffic_note": "ncu dram__bytes per launch, one 32-month sweep of the 20000^2 grid: levels 1-120 (212 M of the "
                                         "220 M non-source cells) move 140.0 GB read + 50.4 GB written in 36.6 ms = 5.2 TB/s, "
                                         "against 204.8 GB algorithmic for the whole sweep (source cells, 45 %, cost no traffic; "
@@ -367,12 +376,14 @@ def main():
     kern_ms = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    launches0 = capi.kernel_launches()
     e0.record()
     for _ in range(a.steps):
         step()
         kern_ms.append(None)
     e1.record()
     fence()
+    launches = capi.kernel_launches() - launches0         # counted by the library at every launch site
     ms_total = e0.elapsed_time(e1)
     last_kernel_ms = basin.last_kernel_ms()
     clocks = sampler.stop() if sampler else None
@@ -388,30 +399,31 @@ def main():
 
     # ---- roofline of the recursion kernel ------------------------------------------------------
     peak_tf = capi.fp64_peak_tflops(4096)
-    peak_rrr = capi.fp64_peak_rrr_tflops(4096)
     units_kernel = float(a.cells) * nloc * a.months
-    ach_tf = units_kernel * FP64_INSTR_PER_UNIT * 2.0 / (kernel_ms * 1e-3) / 1e12
+    rate = units_kernel / (kernel_ms * 1e-3)
+    ach_tf = rate * FLOP_PER_UNIT_ALGO / 1e12                       # algorithmic flops per unit x units / time
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": None,
-                "traffic_note": "ncu --set full on a 1.2e10-unit slice of this workload (profiles/r1_calib2_step3_ncu_full.txt): "
-                                "0.27 GB of DRAM traffic per launch = 0.023 B per unit; the 4.8e11-unit launch is too long to replay",
-                "kernel": "k_gr2m_calib2<fast>" if not a.literal else "k_gr2m_calib2<literal>",
-                "peak_three_register_operand_dfma": peak_rrr,
-                "frac_of_three_register_operand_peak": ach_tf / peak_rrr,
+                "traffic": None, "kernel": "k_gr2m_calib4<cells per thread 2>" if not a.literal else "k_gr2m_calib2<literal>",
                 "kernel_ms": kernel_ms, "units_per_launch": units_kernel,
-                "fp64_instr_per_unit": FP64_INSTR_PER_UNIT,
-                # what actually bounds the kernel: a warp-wide FP64 instruction holds a sub-partition's dispatch
-                # port for two cycles (16 FP64 lanes), every other instruction for one
-                "dispatch_model": dispatch_model(units_kernel, kernel_ms, clocks),
-                "achieved_def": "FP64-pipe instructions issued per unit (SASS count, profiles/) x units x 2 flop "
-                                "(DFMA-slot equivalents) / CUDA-event kernel time",
-                "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak: constant multiplier/addend, "
-                            "2 flop per DFMA); MEASURED_PEAKS.json has no FP64 entry. DFMAs whose three operands are "
-                            "distinct registers sustain only peak_three_register_operand_dfma on this part",
                 "algorithmic_flop_per_unit": FLOP_PER_UNIT_ALGO,
-                "achieved_algorithmic_tflops": units_kernel * FLOP_PER_UNIT_ALGO / (kernel_ms * 1e-3) / 1e12,
-                "survey_ceiling_units_per_s": 7.4e10,
-                "frac_of_survey_ceiling": units_kernel / (kernel_ms * 1e-3) / 7.4e10}
+                "achieved_def": "SURVEY 8(d) algorithmic count (67 FP64 operations per subbasin x set x month, every add / "
+                                "mul / div / compare / exp / cbrt call as 1) x units per launch / CUDA-event kernel time",
+                "peak_def": "DFMA micro-benchmark measured in this run (gr2m_fp64_peak: independent chains, 2 flop per DFMA); "
+                            "MEASURED_PEAKS.json has no FP64 entry and B200_PROFILING.md states none",
+                "pipe_model": pipe_model(units_kernel, kernel_ms, clocks)}
+    if NCU and not a.literal:
+        # executed (not algorithmic) work from the ncu op counters of the shipped kernel; DRAM bytes scale with the units
+        roofline.update({
+            "traffic": (NCU.get("full_launch") or NCU)["dram_bytes_per_unit"] * units_kernel,
+            "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum per launch, measured by ncu on the "
+                           f"{(NCU.get('full_launch') or NCU)['units_per_launch']:.3g}-unit launch of this kernel "
+                           f"({(NCU.get('full_launch') or NCU)['source']}) and scaled by units when the workload differs; "
+                           "algorithmic bytes are ~0 (forcing shared by 8 sets per block and by L2, one outlet sum per set and month)",
+            "executed_flop_per_unit": NCU["executed_flop_per_unit"],
+            "achieved_executed_tflops": rate * NCU["executed_flop_per_unit"] / 1e12,
+            "achieved_executed_def": "2 x DFMA + DMUL + DADD thread instructions per unit from the ncu op counters x units / time",
+            "fp64_pipe_inst_per_unit": NCU["fp64_pipe_inst_per_unit"], "all_inst_per_unit": NCU["all_thread_inst_per_unit"],
+            "fp64_pipe_busy_ncu": NCU["fp64_pipe_busy"], "issue_active_ncu": NCU["issue_active"]})
 
     # ---- end to end through the host-buffer C ABI ---------------------------------------------
     e2e = None
@@ -445,28 +457,38 @@ def main():
             e2e_parts["destroy_s"] += t3 - t2
             return r["of"]
 
-        e2e_step()
-        fence()
-        for k_ in e2e_parts:
-            e2e_parts[k_] = 0.0
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            of_e2e = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        def timed_e2e(pinned):
+            e2e_step()
+            fence()
+            for k_ in e2e_parts:
+                e2e_parts[k_] = 0.0
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                of_ = e2e_step()
+            torch.cuda.synchronize()
+            dt_ = time.perf_counter() - t0
+            tt = torch.tensor([dt_], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), of_, {k_: v_ / n_e2e for k_, v_ in e2e_parts.items()}
+
+        dt, of_e2e, parts = timed_e2e(True)
         same = bool(np.array_equal(of_e2e, of_host[s0:s1], equal_nan=True))
         e2e = {"value": units_step * n_e2e / dt, "unit": UNIT,
                "h2d_bytes_per_step": int((P.nbytes + E.nbytes) // world + area.nbytes + nd.nbytes + region.nbytes + par.nbytes
                                          + qobs.nbytes),
                "h2d_note": "per rank" + ("; forcing rows uploaded 1/%d per rank and all-gathered (NCCL)" % world if world > 1 else ""),
                "d2h_bytes_per_step": int(nloc * 8), "steps": n_e2e, "matches_resident_run": same,
-               "seconds_per_step": {k_: v_ / n_e2e for k_, v_ in e2e_parts.items()},
+               "seconds_per_step": parts,
                "api": ("dist.replicate_forcing + gr2m_basin_create_dev" if world > 1 else "gr2m_basin_create")
                       + " + gr2m_objective_batch + gr2m_basin_destroy (pinned host buffers)"}
+        if world == 1:
+            # what an R caller has: ordinary pageable matrices (the library stages them through its pinned ring)
+            Pp, Ep, parp = torch.from_numpy(P), torch.from_numpy(E), torch.from_numpy(par)
+            dtp, of_p, parts_p = timed_e2e(False)
+            e2e["pageable"] = {"value": units_step * n_e2e / dtp, "unit": UNIT, "seconds_per_step": parts_p,
+                               "matches_resident_run": bool(np.array_equal(of_p, of_host[s0:s1], equal_nan=True)),
+                               "note": "same call sequence on pageable host arrays, as .Call from R passes them"}
     else:
         basin.close()
 
@@ -484,7 +506,8 @@ def main():
             simulation = {"metric": "gr2m_cell_months_per_sec (simulation mode, 1 set, PR/AE/SM/RU/QS written)",
                           "workload": f"{a.cells} subbasins x {a.months} months x 1 parameter set",
                           "kernel_ms": kms, "kernel_value": u / (kms * 1e-3),
-                          "e2e_value": u / dt, "e2e_note": "gr2m_run incl. 5 transposes and 5 x D2H of [ntime x ncell] doubles",
+                          "e2e_value": u / dt, "e2e_note": "gr2m_run on pageable host arrays: kernel writes R's layout, 5 x D2H of "
+                                                           "[ntime x ncell] doubles staged through the pinned ring",
                           "roofline": {"bound": "hbm", "achieved": u * 56.0 / (kms * 1e-3) / 1e9, "unit": "GB/s",
                                        "algorithmic_bytes_per_unit": 56,
                                        "note": "launch-latency sized (one thread per subbasin): reported, not tuned"}}
@@ -508,9 +531,15 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "sets_per_gpu": nloc, "objective": "KGE", "warmup_months": 36,
                            "l2": "forcing (768 MB) and outlet partials larger than L2; no flush needed",
-                           "parallelism": f"parameter sets sharded over {world} GPU(s), forcing replicated"},
+                           "parallelism": f"parameter sets sharded over {world} GPU(s), forcing replicated",
+                           "reference_arm_note": "bench.py --impl reference is the CPU oracle PORT (R / airGR / TauDEM cannot run in "
+                                                 "this image) on a bounded DOWN-SCALED sample of this workload (2 000 subbasins x "
+                                                 "as many sets as fit ~15 s x all months), rate-extrapolated: a lower bound on the "
+                                                 "reference's time, not the same configuration"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": 2 * a.steps, "clocks": clocks, "routing": routing, "simulation": simulation,
+                "gpu_launches": launches,
+                "gpu_launches_note": "kernels of libgr2m_b200 launched by this rank inside the timed region, counted by the library "
+                                     "itself (gr2m_kernel_launches); per step: k_gr2m_calib4 + k_objective", "clocks": clocks, "routing": routing, "simulation": simulation,
                 "objective_checksum": float(np.nansum(of_host))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,6 +1,10 @@
-"""Summarise an .ncu-rep (read here, no GPU needed): python scripts/ncu_summary.py rep.ncu-rep units_per_launch > profiles/x.txt"""
-import csv, io, subprocess, sys
+"""Summarise an .ncu-rep (read here, no GPU needed):
+    python scripts/ncu_summary.py rep.ncu-rep units_per_launch [counters.json] > profiles/x.txt
+With a third argument the per-unit counters bench.py quotes (instructions, executed flops, DRAM bytes, pipe
+utilisation) are also written as JSON."""
+import csv, io, json, os, subprocess, sys
 rep, units = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else None
+jout = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, unit = rows[0], rows[1]
@@ -43,3 +47,23 @@ for r in rows[2:]:
         print(f"   DFMA+DMUL+DADD thread instructions per unit : {f * cyc / units:8.2f}")
         print(f"   all thread instructions per unit            : {tot / units:8.2f}")
         print(f"   units per second                            : {units / (float(d['gpu__time_duration.sum'].replace(',', '')) * 1e-3):.4g}" if u.get('gpu__time_duration.sum') == 'ms' else "")
+        if jout:
+            g = lambda k: float(d[k].replace(",", ""))
+            per = {o: g(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum.per_cycle_elapsed") * cyc / units for o in ("dfma", "dmul", "dadd")}
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            dram = sum(g(k) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            busy = g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100.0
+            # FP64-pipe warp instructions: the pipe is busy 2 cycles per warp instruction on each of the 4 sub-partitions
+            pipe_inst = busy * g("sm__cycles_active.avg") * 4 / 2.0 * 32 * g("launch__sm_count") / units if "sm__cycles_active.avg" in d and "launch__sm_count" in d else None
+            json.dump({"source": os.path.basename(rep), "kernel": d["Kernel Name"], "units_per_launch": units,
+                       "kernel_ms_under_ncu": g("gpu__time_duration.sum"),
+                       "dfma_per_unit": per["dfma"], "dmul_per_unit": per["dmul"], "dadd_per_unit": per["dadd"],
+                       "executed_flop_per_unit": 2 * per["dfma"] + per["dmul"] + per["dadd"],
+                       "fp64_pipe_inst_per_unit": pipe_inst if pipe_inst else f * cyc / units,
+                       "fp64_pipe_inst_def": "DFMA + DMUL + DADD + DSETP: FP64-pipe busy cycles / 2 per warp instruction x 32 lanes / units" if pipe_inst else "DFMA + DMUL + DADD only",
+                       "all_thread_inst_per_unit": tot / units,
+                       "fp64_pipe_busy": busy, "issue_active": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                       "xu_pipe_busy": g("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active") / 100.0,
+                       "dram_bytes_per_launch": dram, "dram_bytes_per_unit": dram / units,
+                       "registers": int(g("launch__registers_per_thread")), "smem_per_block_kb": g("launch__shared_mem_per_block_dynamic")},
+                      open(jout, "w"), indent=1)
