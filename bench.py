@@ -70,6 +70,10 @@ def parse_args():
     ap.add_argument("--route-n", type=int, default=20_000, help="side of the synthetic D8 grid (0 = skip routing)")
     ap.add_argument("--route-batch", type=int, default=32, help="months per routing batch")
     ap.add_argument("--route-flags", type=int, default=0, help="WFA_* flags for the routing sweep")
+    ap.add_argument("--route-terrain", default="both", choices=["tilted", "filled", "both"],
+                    help="tilted: plane + roughness below the tilt (no depressions, round-1 grid); filled: SURVEY 8(d) terrain, "
+                         "plane + 5 octaves of value noise with slopes comparable to the tilt, depressions filled and D8 derived "
+                         "by wfa_flowdir_from_dem on the device")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--literal", action="store_true", help="use the literal (IEEE division) kernel variant")
@@ -223,13 +227,25 @@ def bench_router(a, capi, torch, plan, n, months, dense_ms_one_gpu):
                     "polygon cell lists and is paid once per geometry"}
 
 
-def bench_routing(a, capi, torch, rank, world, dist):
+def bench_routing(a, capi, torch, rank, world, dist, terrain="tilted"):
     """Secondary metric: batched WFA sweep, months sharded across ranks (plan replicated)."""
     from gr2msemidistr_b200 import synth
     n = a.route_n
     dev = torch.device("cuda", torch.cuda.current_device())
     t0 = time.perf_counter()
-    d8 = synth.d8_grid(n, n, device=dev)
+    lake_share = None
+    if terrain == "filled":
+        z, valid = synth.fractal_dem(n, n, device=dev)
+        v8 = valid.to(torch.uint8).contiguous()
+        del valid
+        d8 = torch.empty((n, n), dtype=torch.int16, device=dev)
+        filled = torch.empty((n, n), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        capi.flowdir_from_dem_dev(z.data_ptr(), v8.data_ptr(), n, n, d8.data_ptr(), filled.data_ptr())
+        lake_share = float(((filled > z + 1e-9) & (v8 != 0)).double().mean().item())
+        del z, v8, filled
+    else:
+        d8 = synth.d8_grid(n, n, device=dev)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -272,10 +288,14 @@ def bench_routing(a, capi, torch, rank, world, dist):
     gbs = units / world * 16.0 / (ms * 1e-3) / 1e9
     # DRAM bytes per 32-month pass from the ncu launch list of the same grid (profiles/r1_wide_levels_traffic.txt): the wide
     # levels move 190.4 GB = 14.9 B per grid cell and month; scaled to this pass's cells x months
-    traffic = 190.4e9 / (4.0e8 * 32) * float(ncell) * my_months if n == 20000 else None
+    traffic = 190.4e9 / (4.0e8 * 32) * float(ncell) * my_months if (n == 20000 and terrain == "tilted") else None
     out = {"metric": "routed_cell_months_per_sec", "value": units / (ms * 1e-3), "unit": UNIT,
            "workload": f"C5 WFA: {n} x {n} synthetic D8 grid x {months_total} months, dense FP64 weights, "
                        f"{ld}-month batches, months sharded over {world} GPU(s)",
+           "terrain": ("plane tilted to the south-east + 5 octaves of value noise with slopes comparable to the tilt, closed "
+                       f"depressions filled ({100 * lake_share:.1f} % of the cells raised) and D8 derived on the device "
+                       "(wfa_flowdir_from_dem_dev; SURVEY 8(d))") if terrain == "filled" else
+                      "plane tilted to the south-east + roughness below the tilt (no depressions to fill; round-1 grid)",
            "ms_per_pass": ms, "levels": plan.nlevels, "cells_in_order": plan.norder,
            "plan_build_s": t_plan, "grid_gen_s": t_gen,
            "value_incl_plan_build": units / (ms * 1e-3 + t_plan),
@@ -295,13 +315,13 @@ def bench_routing(a, capi, torch, rank, world, dist):
     out["reaches"] = plan.reach_info()
     del A
     torch.cuda.empty_cache()
-    if rank == 0:
+    if rank == 0 and terrain == "tilted":
         try:
             out["operator"] = bench_router(a, capi, torch, plan, n, months_total, ms * world)
         except Exception as ex:       # secondary figure: report, do not lose the sweep number
             out["operator"] = {"error": repr(ex)}
     plan.close()
-    if rank == 0 and not a.no_cpu:
+    if rank == 0 and not a.no_cpu and terrain == "tilted":
         out["cpu_baseline"] = cpu_routing(a)
     return out
 
@@ -514,12 +534,18 @@ def main():
         except Exception as ex:
             simulation = {"error": repr(ex)}
 
-    routing = None
-    if a.route_n > 0:
+    routing, routing_filled = None, None
+    if a.route_n > 0 and a.route_terrain in ("tilted", "both"):
         try:
-            routing = bench_routing(a, capi, torch, rank, world, dist)
+            routing = bench_routing(a, capi, torch, rank, world, dist, "tilted")
         except Exception as ex:   # report, do not lose the headline line
             routing = {"error": repr(ex)}
+    if a.route_n > 0 and a.route_terrain in ("filled", "both"):
+        try:
+            capi.release_cached_memory()
+            routing_filled = bench_routing(a, capi, torch, rank, world, dist, "filled")
+        except Exception as ex:
+            routing_filled = {"error": repr(ex)}
 
     cpu = None
     if rank == 0 and not a.no_cpu:
@@ -539,7 +565,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches,
                 "gpu_launches_note": "kernels of libgr2m_b200 launched by this rank inside the timed region, counted by the library "
-                                     "itself (gr2m_kernel_launches); per step: k_gr2m_calib4 + k_objective", "clocks": clocks, "routing": routing, "simulation": simulation,
+                                     "itself (gr2m_kernel_launches); per step: k_gr2m_calib4 + k_objective", "clocks": clocks, "routing": routing, "routing_filled_terrain": routing_filled, "simulation": simulation,
                 "objective_checksum": float(np.nansum(of_host))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,7 +29,7 @@ SYMBOLS = (
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_router_create", "wfa_router_destroy",
     "wfa_router_info", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
-    "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem",
+    "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem", "wfa_flowdir_from_dem_dev",
 )
 
 
@@ -375,6 +375,12 @@ def flowdir_from_dem(dem, valid, want_filled: bool = False):
     _check(lib().wfa_flowdir_from_dem(_dp(z), v.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int(z.shape[0]),
                                       C.c_int(z.shape[1]), fd.ctypes.data_as(C.POINTER(C.c_int16)), _dp(filled)))
     return (fd, filled) if want_filled else fd
+
+
+def flowdir_from_dem_dev(dem_ptr: int, valid_ptr: int, nrow: int, ncol: int, flowdir_ptr: int, filled_ptr: int = 0):
+    """Device-pointer variant: dem float64, valid uint8, flowdir int16 (out), filled float64 (out, optional)."""
+    _check(lib().wfa_flowdir_from_dem_dev(C.c_void_p(dem_ptr), C.c_void_p(valid_ptr), C.c_int(nrow), C.c_int(ncol),
+                                          C.c_void_p(flowdir_ptr), C.c_void_p(filled_ptr or 0)))
 
 
 def debug_math(op: int, x, y=None):

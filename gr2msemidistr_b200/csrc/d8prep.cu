@@ -128,8 +128,9 @@ __global__ void k_d8_finish(const uint8_t *__restrict__ valid, size_t n, int16_t
 
 }  // namespace
 
-extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int nrow, int ncol, int16_t *flowdir,
-                                    double *filled)
+// dem / valid / flowdir / filled are host pointers, or device pointers when on_device
+static int flowdir_common(const double *dem, const uint8_t *valid, int nrow, int ncol, int16_t *flowdir, double *filled,
+                          bool on_device)
 {
     REQUIRE(dem && valid && flowdir, "NULL argument");
     REQUIRE(nrow > 0 && ncol > 0, "nrow and ncol must be positive");
@@ -141,15 +142,20 @@ extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int
     auto release = [&]() { FreeBatch fb; for (DevBuf *b : {&bz, &bF, &bv, &be, &bc, &bd, &bflag}) b->release(); };
 #define DCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); release(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
 #define DRC(call) do { int r_ = (call); if (r_) { release(); return r_; } } while (0)
-    DRC(bz.ensure(n * 8)); DRC(bF.ensure(n * 8)); DRC(bv.ensure(n)); DRC(be.ensure(n)); DRC(bc.ensure(n * 2));
-    DRC(bd.ensure(n * 4)); DRC(bflag.ensure(sizeof(int)));
-    double *dz = bz.as<double>(), *dF = bF.as<double>();
-    uint8_t *dv = bv.as<uint8_t>(), *de = be.as<uint8_t>();
-    int16_t *dc = bc.as<int16_t>();
+    if (!on_device) { DRC(bz.ensure(n * 8)); DRC(bv.ensure(n)); DRC(bc.ensure(n * 2)); }
+    if (!on_device || !filled) DRC(bF.ensure(n * 8));
+    DRC(be.ensure(n)); DRC(bd.ensure(n * 4)); DRC(bflag.ensure(sizeof(int)));
+    const double *dz = on_device ? dem : bz.as<double>();
+    const uint8_t *dv = on_device ? valid : bv.as<uint8_t>();
+    double *dF = (on_device && filled) ? filled : bF.as<double>();
+    uint8_t *de = be.as<uint8_t>();
+    int16_t *dc = on_device ? flowdir : bc.as<int16_t>();
     int32_t *dd = bd.as<int32_t>();
     int *dflag = bflag.as<int>();
-    DCK(cudaMemcpy(dz, dem, n * 8, cudaMemcpyHostToDevice));
-    DCK(cudaMemcpy(dv, valid, n, cudaMemcpyHostToDevice));
+    if (!on_device) {
+        DCK(cudaMemcpy(bz.p, dem, n * 8, cudaMemcpyHostToDevice));
+        DCK(cudaMemcpy(bv.p, valid, n, cudaMemcpyHostToDevice));
+    }
     dim3 rowgrid(ceil_div(ncol, 256), nrow);
     gr2m_count_launch(), k_d8_init<<<rowgrid, 256>>>(dz, dv, nrow, ncol, dF, de);
     DCK(cudaGetLastError());
@@ -172,10 +178,26 @@ extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int
     }
     gr2m_count_launch(), k_d8_finish<<<ceil_div((long long)n, 256), 256>>>(dv, n, dc, filled ? dF : nullptr);
     DCK(cudaGetLastError());
-    DCK(cudaMemcpy(flowdir, dc, n * 2, cudaMemcpyDeviceToHost));
-    if (filled) DCK(cudaMemcpy(filled, dF, n * 8, cudaMemcpyDeviceToHost));
+    if (!on_device) {
+        DCK(cudaMemcpy(flowdir, dc, n * 2, cudaMemcpyDeviceToHost));
+        if (filled) DCK(cudaMemcpy(filled, dF, n * 8, cudaMemcpyDeviceToHost));
+    } else {
+        DCK(cudaDeviceSynchronize());
+    }
 #undef DCK
 #undef DRC
     release();
     return GR2M_OK;
+}
+
+extern "C" int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int nrow, int ncol, int16_t *flowdir,
+                                    double *filled)
+{
+    return flowdir_common(dem, valid, nrow, ncol, flowdir, filled, false);
+}
+
+extern "C" int wfa_flowdir_from_dem_dev(const double *dem_dev, const uint8_t *valid_dev, int nrow, int ncol,
+                                        int16_t *flowdir_dev, double *filled_dev)
+{
+    return flowdir_common(dem_dev, valid_dev, nrow, ncol, flowdir_dev, filled_dev, true);
 }

@@ -131,6 +131,43 @@ def d8_grid(nrow: int, ncol: int, seed: int = SEED + 3, device="cpu", nodata_fra
     return code
 
 
+def fractal_dem(nrow: int, ncol: int, seed: int = SEED + 4, device="cpu", nodata_frac: float = 0.02, octaves: int = 5,
+                relief: float = 1.0):
+    """SURVEY 8(d) terrain: plane tilted to the south-east + `octaves` octaves of value noise whose local slopes
+    are comparable to the tilt (so the surface is full of closed depressions and the drainage meanders), 2 % nodata in
+    64 x 64 blocks plus the outer ring.  Returns (z float64 [nrow, ncol], valid bool) torch tensors on `device`;
+    wfa_flowdir_from_dem fills it and derives the D8 grid."""
+    import torch
+    import torch.nn.functional as F
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = torch.device(device)
+    rr = torch.arange(nrow, device=dev, dtype=torch.float32)[:, None]
+    cc = torch.arange(ncol, device=dev, dtype=torch.float32)[None, :]
+    z = -(0.55 * rr + 0.45 * cc)
+    # wavelengths 1024, 256, 64, 16, 4 cells; amplitude relief x tilt x wavelength: an octave's slope reaches relief x the tilt
+    # where neighbouring lattice values differ by 1 (typical: a third of that); relief = 1 leaves ~4 % of a 20 000^2 grid in lakes
+    for o in range(octaves):
+        lam = 1024 // (4 ** o)
+        if lam < 2:
+            break
+        hr, hc = nrow // lam + 3, ncol // lam + 3
+        coarse = torch.rand((1, 1, hr, hc), generator=g).to(dev)
+        z = z + (relief * 0.71 * lam) * F.interpolate(coarse, size=(nrow, ncol), mode="bicubic", align_corners=True)[0, 0]
+        del coarse
+    hb = (rr.to(torch.int64) // 64) * 40503 + (cc.to(torch.int64) // 64) * 9973 + (seed & 0xFFFF)
+    hb = (hb * 2654435761) & 0xFFFFFFFF
+    hb = ((hb ^ (hb >> 15)) * 2246822519) & 0xFFFFFFFF
+    hb = (hb ^ (hb >> 13)) & 0xFFFFFFFF
+    hole = hb.to(torch.float32) / 4294967296.0 < nodata_frac
+    del hb
+    hole[0, :] = True
+    hole[-1, :] = True
+    hole[:, 0] = True
+    hole[:, -1] = True
+    return z.to(torch.float64), ~hole
+
+
 def block_polygons(nrow: int, ncol: int, nby: int, nbx: int, margin: int = 1):
     """Synthetic 'subbasin polygons': an nby x nbx tiling of the grid. Returns (src_cell [nsub],
     poly_off [nsub+1], poly_cells) with 0-based row-major cell ids: src = block centre (the

@@ -209,6 +209,9 @@ int wfa_plan_last_phase_ms(wfa_plan *p, float *wide_ms, float *tail_ms);
  * this library's own (see csrc/d8prep.cu); any D8 grid, e.g. TauDEM's, can be given to wfa_plan_create. */
 int wfa_flowdir_from_dem(const double *dem, const uint8_t *valid, int nrow, int ncol, int16_t *flowdir,
                          double *filled);
+/* Same with every array already in device memory (blocking; the result can go straight to wfa_plan_create_dev). */
+int wfa_flowdir_from_dem_dev(const double *dem_dev, const uint8_t *valid_dev, int nrow, int ncol, int16_t *flowdir_dev,
+                             double *filled_dev);
 
 #ifdef __cplusplus
 }

@@ -51,3 +51,24 @@ def test_edge_cases(capi):
     z = np.add.outer(np.arange(40.0), np.arange(50.0)); z[10:30, 10:40] = 5.0
     _check(capi, z)                                          # a plateau cut into a slope (a pit to fill)
     _check(capi, np.arange(12.0)[None, :])                   # one row
+
+
+def test_device_pointer_variant_and_fractal_terrain(capi):
+    # the survey-spec terrain of bench.py --route-terrain filled, small: device-resident call == host call == CPU rule
+    import torch
+    from gr2msemidistr_b200 import synth
+    dev = torch.device("cuda", 0)
+    z, valid = synth.fractal_dem(150, 210, device=dev, relief=10.0)      # steep enough for many depressions on a small grid
+    v8 = valid.to(torch.uint8).contiguous()
+    fd = torch.empty((150, 210), dtype=torch.int16, device=dev)
+    filled = torch.empty((150, 210), dtype=torch.float64, device=dev)
+    capi.flowdir_from_dem_dev(z.data_ptr(), v8.data_ptr(), 150, 210, fd.data_ptr(), filled.data_ptr())
+    zh, vh = z.cpu().numpy(), valid.cpu().numpy()
+    want_f, want_fd = d8prep.fill_and_flowdir(np.where(vh, zh, np.nan))
+    assert np.array_equal(fd.cpu().numpy(), want_fd)
+    assert np.array_equal(np.nan_to_num(filled.cpu().numpy(), nan=-9e9), np.nan_to_num(want_f, nan=-9e9))
+    assert np.array_equal(capi.flowdir_from_dem(np.where(vh, zh, 0.0), vh), want_fd)
+    assert np.any((want_f > zh + 1e-9)[vh])                    # there was something to fill
+    fd2 = torch.empty_like(fd)
+    capi.flowdir_from_dem_dev(z.data_ptr(), v8.data_ptr(), 150, 210, fd2.data_ptr())      # without the filled surface
+    assert torch.equal(fd, fd2)
