@@ -19,6 +19,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4
 PERC_F32_EXPONENT, SINK_UNROUNDED, MATH_LITERAL = 1, 8, 16
 OF_KGE, OF_NSE, OF_RMSE = 0, 1, 2
 WFA_F32, WFA_NO_CONTAMINATION, WFA_LEVEL_SYNC, WFA_DATAFLOW, WFA_NO_FORWARD, WFA_BY_BASIN, WFA_ROUTE_DENSE, WFA_NO_OVERLAP = 1, 2, 4, 8, 16, 32, 64, 128
+WFA_NO_SEGMENTS = 256
 OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 
 # every symbol include/gr2m_b200.h declares (tests check the library exports exactly these)
@@ -27,7 +28,7 @@ SYMBOLS = (
     "gr2m_basin_create", "gr2m_basin_create_dev", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
-    "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_router_create", "wfa_router_destroy",
+    "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_plan_segment_info", "wfa_router_create", "wfa_router_destroy",
     "wfa_router_info", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
     "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem", "wfa_flowdir_from_dem_dev",
 )
@@ -310,6 +311,11 @@ class Plan:
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().wfa_plan_reach_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(nreaches=a.value, nreach_levels=b.value, critical_cells=c.value, enabled=bool(d.value))
+
+    def segment_info(self):
+        a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_int()
+        _check(lib().wfa_plan_segment_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(nsegments=a.value, ncells=b.value, levels=c.value, enabled=bool(d.value))
 
     def last_phase_ms(self):
         a, b = C.c_float(), C.c_float()

@@ -227,6 +227,178 @@ __device__ __forceinline__ void accum_cell2(int32_t c0, unsigned m0, int32_t c1,
     }
 }
 
+// ---- chain segments ---------------------------------------------------------------------------------
+// Most cells below the cut have exactly one upstream cell that is not a source (level 0): their sum is the
+// predecessor's sum plus their own weight (plus source weights).  A level sweep re-reads that predecessor row from
+// DRAM one launch after it was written: 8 of the 24 bytes a non-source cell moves per month.  Such cells are
+// ABSORBED into the lane group that computes their predecessor: a segment is a head cell (computed like in
+// k_accum_level) followed by up to SEG_K - 1 absorbed cells along the flow path, the running sum staying in
+// registers.  Segments are cut where the level index is 1 modulo SEG_K, so a segment never exceeds SEG_K cells and
+// needs no position bookkeeping; a segment is launched with its head's level, which is never later than the level
+// any of its cells had, so every dependency of every later launch is still met.  Additions keep TauDEM's k order
+// (the predecessor's value enters at its own k), so the sums are the same bits as the level sweep's.
+constexpr int SEG_K = 2;
+constexpr int SEG_PF = 8192;      // descriptors are prefetched into L2 this many segments ahead
+struct SegDesc {
+    int32_t head;
+    uint8_t len, hmask;
+    uint16_t step[SEG_K - 1];      // per absorbed cell: (flow direction of the previous cell - 1) | in-flow mask << 3
+};
+static_assert(sizeof(SegDesc) == 4 + 2 * SEG_K && (SEG_K % 2) == 0, "SegDesc is 1 + SEG_K / 2 words of 32 bits");
+
+// absorbable: level in [2, seg_levels), exactly one upstream cell above level 0, and not at a segment boundary
+__device__ __forceinline__ bool seg_absorbed(int32_t c, int lev, int seg_levels, int ncol, const uint8_t *__restrict__ inmask,
+                                             const int32_t *__restrict__ level)
+{
+    if (lev < 2 || lev >= seg_levels || (lev - 1) % SEG_K == 0) return false;
+    unsigned m = inmask[c];
+    int nhigh = 0;
+    while (m) {
+        int k = __ffs(m);
+        m &= m - 1;
+        nhigh += level[c + c_dy[k] * ncol + c_dx[k]] >= 1;
+    }
+    return nhigh == 1;
+}
+
+// flag[i] = 1 iff order[i] (i in [begin, end)) starts a segment
+__global__ void k_seg_flag(const int32_t *__restrict__ order, int begin, int end, int seg_levels, int ncol,
+                           const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level, int32_t *__restrict__ flag)
+{
+    int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const int32_t c = order[i];
+    flag[i - begin] = seg_absorbed(c, level[c], seg_levels, ncol, inmask, level) ? 0 : 1;
+}
+
+// heads write their descriptor at the slot the scan gave them
+__global__ void k_seg_build(const int32_t *__restrict__ order, int begin, int end, int seg_levels, int ncol,
+                            const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level,
+                            const int32_t *__restrict__ receiver, const int32_t *__restrict__ flag,
+                            const int32_t *__restrict__ slot, SegDesc *__restrict__ segs, unsigned long long *ncells)
+{
+    int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end || !flag[i - begin]) return;
+    int32_t c = order[i];
+    SegDesc d;
+    d.head = c; d.hmask = inmask[c];
+    int len = 1;
+    for (int s = 0; s < SEG_K - 1; ++s) d.step[s] = 0;
+    while (len < SEG_K) {
+        const int32_t r = receiver[c];
+        if (r < 0) break;
+        const int lr = level[r];
+        if (!seg_absorbed(r, lr, seg_levels, ncol, inmask, level)) break;
+        // the cell r absorbs from is its only upstream cell above level 0: that must be c (c is above level 0)
+        const int dr = r / ncol - c / ncol, dc = r % ncol - c % ncol;
+        int kd = 0;
+        for (int k = 1; k <= 8; ++k) if (c_dy[k] == dr && c_dx[k] == dc) kd = k;
+        d.step[len - 1] = (uint16_t)((kd - 1) | (inmask[r] << 3));
+        c = r;
+        ++len;
+    }
+    d.len = (uint8_t)len;
+    segs[slot[i - begin] - 1] = d;
+    atomicAdd(ncells, (unsigned long long)len);
+}
+
+// One lane group per segment, months on the lanes.  Everything that does not depend on earlier launches (the
+// descriptor, the weights of all cells of the segment, the source rows flowing into its absorbed cells) is requested
+// before griddepcontrol.wait, all loads first and the additions afterwards so that a lane has up to 3 SEG_K rows in
+// flight; only the head's upstream rows wait for the previous level.
+template <typename T, int G>
+__global__ void __launch_bounds__(256, 8) k_accum_segments(const SegDesc *__restrict__ segs, int begin, int end, int ncol, T *A,
+                                                           int ld, int nmonth)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, g = threadIdx.x % G;
+    const int si = begin + gid;
+    const bool live = si < end;
+    // descriptors are read once, in order: pull the ones a later block of this launch will want into L2 now
+    if (threadIdx.x == 0 && si + SEG_PF < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(segs + si + SEG_PF));
+    int32_t cell[SEG_K];
+    unsigned st[SEG_K];          // per absorbed cell: (kd - 1) | in-flow mask << 3; st[0]: the head's in-flow mask
+    int len = 0;
+    if (live) {
+        const int32_t *w = reinterpret_cast<const int32_t *>(segs + si);
+        unsigned wd[1 + SEG_K / 2];                        // head | len, hmask, step[0] | step[1], step[2] | ...
+#pragma unroll
+        for (int q = 0; q < 1 + SEG_K / 2; ++q) wd[q] = (unsigned)__ldg(w + q);
+        cell[0] = (int32_t)wd[0];
+        len = wd[1] & 0xff;
+        st[0] = (wd[1] >> 8) & 0xff;
+#pragma unroll
+        for (int i = 1; i < SEG_K; ++i) st[i] = (i & 1) ? wd[(i + 1) / 2] >> 16 : wd[(i + 2) / 2] & 0xffff;
+#pragma unroll
+        for (int i = 1; i < SEG_K; ++i) {
+            const int kd = (st[i] & 7) + 1;
+            cell[i] = cell[i - 1] + c_dy[kd] * ncol + c_dx[kd];
+        }
+    }
+    for (int jb = 0; jb < nmonth; jb += G) {
+        const int j = jb + g;
+        const bool on = live && j < nmonth;
+        // phase 1, loads only: own weights; per absorbed cell the first source row below the predecessor's k and the
+        // first one above it (sources are level-0 cells: their rows are never written)
+        T low[SEG_K], s1[SEG_K], h1[SEG_K];
+#pragma unroll
+        for (int i = 0; i < SEG_K; ++i) {
+            low[i] = T(0);
+            if (on && i < len) low[i] = __ldcs(A + (size_t)cell[i] * ld + j);
+        }
+#pragma unroll
+        for (int i = 1; i < SEG_K; ++i) {
+            s1[i] = T(0); h1[i] = T(0);
+            if (on && i < len) {
+                const unsigned kp = (((st[i] & 7) + 4) & 7) + 1, m = st[i] >> 3;      // predecessor seen from this cell
+                const unsigned lo = m & ((1u << (kp - 1)) - 1), hi = m & ~((1u << kp) - 1);
+                if (lo) s1[i] = __ldcs(up_row(A, cell[i], __ffs(lo), ncol, ld) + j);
+                if (hi) h1[i] = __ldcs(up_row(A, cell[i], __ffs(hi), ncol, ld) + j);
+            }
+        }
+        if (jb == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!on) continue;
+        // the head like any cell of a level sweep (its upstream rows were written by earlier launches) ...
+        T acc = low[0];
+        {
+            unsigned mm = st[0];
+            while (mm) {
+                acc += __ldcg(up_row(A, cell[0], __ffs(mm), ncol, ld) + j);
+                mm &= mm - 1;
+            }
+        }
+        A[(size_t)cell[0] * ld + j] = acc;
+        // ... then the running sum down the segment, additions in k order: sources below the predecessor, the
+        // predecessor (in registers), sources above it
+#pragma unroll
+        for (int i = 1; i < SEG_K; ++i) {
+            if (i < len) {
+                const unsigned kp = (((st[i] & 7) + 4) & 7) + 1, m = st[i] >> 3;
+                unsigned lo = m & ((1u << (kp - 1)) - 1), hi = m & ~((1u << kp) - 1);
+                T v = low[i];
+                if (lo) {
+                    v += s1[i];
+                    lo &= lo - 1;
+                    while (lo) {                 // a second source below the predecessor: rare
+                        v += __ldcs(up_row(A, cell[i], __ffs(lo), ncol, ld) + j);
+                        lo &= lo - 1;
+                    }
+                }
+                acc = v + acc;
+                if (hi) {
+                    acc += h1[i];
+                    hi &= hi - 1;
+                    while (hi) {
+                        acc += __ldcs(up_row(A, cell[i], __ffs(hi), ncol, ld) + j);
+                        hi &= hi - 1;
+                    }
+                }
+                A[(size_t)cell[i] * ld + j] = acc;
+            }
+        }
+    }
+}
+
 // one wide level per launch, two cells per lane group (cells of a level never feed each other).
 // Launched with programmatic stream serialization: the CTAs of level l+1 may become resident while level
 // l drains; they read their topology and pull their own rows (weights, never written by another level)
@@ -1157,7 +1329,7 @@ static void plan_free(wfa_plan *p)
     DevBuf *bufs[] = {&p->receiver, &p->inmask, &p->omask, &p->indeg, &p->level, &p->order, &p->level_off, &p->contam,
                       &p->tailmask, &p->done, &p->ticket, &p->work, &p->work2, &p->qs, &p->src, &p->poff, &p->pcells,
                       &p->qr, &p->corder, &p->cmask, &p->cnext, &p->comps, &p->cup_off, &p->cup_idx, &p->rcell, &p->rup_off,
-                      &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo, &p->rdone};
+                      &p->rup_idx, &p->run_start, &p->row_off, &p->rowcell, &p->rstream, &p->rinfo, &p->rdone, &p->segs};
     { FreeBatch fb; for (DevBuf *d : bufs) d->release(); }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1168,6 +1340,7 @@ static void plan_free(wfa_plan *p)
 
 static int plan_build_components(wfa_plan *p);
 static int plan_build_runs(wfa_plan *p);
+static int plan_build_segments(wfa_plan *p);
 
 static int plan_build(wfa_plan *p, const int16_t *dir_dev)
 {
@@ -1379,7 +1552,9 @@ static int plan_build_components(wfa_plan *p)
     cleanup();
 #undef QCK
 #undef QRC
-    return plan_build_runs(p);
+    int rc_runs = plan_build_runs(p);
+    if (rc_runs) return rc_runs;
+    return plan_build_segments(p);
 }
 
 
@@ -1544,6 +1719,72 @@ static int plan_build_runs(wfa_plan *p)
 }
 
 
+__global__ void k_seg_offsets(const int32_t *__restrict__ level_off, int begin, int nlev, const int32_t *__restrict__ slot,
+                              int32_t *__restrict__ seg_off)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;      // seg_off[l] = heads before level l, l = 1 .. nlev
+    if (l < 1 || l > nlev) return;
+    const int pos = level_off[l] - begin;
+    seg_off[l] = pos > 0 ? slot[pos - 1] : 0;
+}
+
+// Chain segments of the levels [1, comp_level) (see k_accum_segments).  Optional: on any failure the level sweep stays.
+static int plan_build_segments(wfa_plan *p)
+{
+    p->seg_ok = false;
+    p->nseg = p->nseg_cells = 0;
+    static const bool off_env = getenv("WFA_NO_SEGMENTS") != nullptr;
+    const int L = p->comp_level;
+    if (off_env || !(p->run_ok || p->comp_ok) || L <= 2) return GR2M_OK;
+    cudaStream_t st = p->stream;
+    const std::vector<int32_t> &off = p->h_level_off;
+    const int begin = off[1], end = off[L], n = end - begin;
+    if (n <= 0) return GR2M_OK;
+    DevBuf flag, slot, temp, segoff, cnt;
+    auto cleanup = [&]() { FreeBatch fb; for (DevBuf *b : {&flag, &slot, &temp, &segoff, &cnt}) b->release(); };
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
+#define SRC(call) do { int r_ = (call); if (r_) { cleanup(); return r_; } } while (0)
+    SRC(flag.ensure((size_t)n * 4)); SRC(slot.ensure((size_t)n * 4)); SRC(segoff.ensure(((size_t)L + 2) * 4)); SRC(cnt.ensure(8));
+    gr2m_count_launch(), k_seg_flag<<<ceil_div(n, 256), 256, 0, st>>>(p->order.as<int32_t>(), begin, end, L, p->ncol, p->inmask.as<uint8_t>(),
+                                                                     p->level.as<int32_t>(), flag.as<int32_t>());
+    SCK(cudaGetLastError());
+    size_t tbytes = 0;
+    SCK(cub::DeviceScan::InclusiveSum(nullptr, tbytes, flag.as<int32_t>(), slot.as<int32_t>(), n, st));
+    SRC(temp.ensure(tbytes));
+    SCK(cub::DeviceScan::InclusiveSum(temp.p, tbytes, flag.as<int32_t>(), slot.as<int32_t>(), n, st));
+    int32_t nseg = 0;
+    SCK(cudaMemcpyAsync(&nseg, slot.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    if (nseg <= 0) { cleanup(); return GR2M_OK; }
+    SRC(p->segs.ensure((size_t)nseg * sizeof(SegDesc)));
+    SCK(cudaMemsetAsync(cnt.p, 0, 8, st));
+    gr2m_count_launch(), k_seg_build<<<ceil_div(n, 256), 256, 0, st>>>(p->order.as<int32_t>(), begin, end, L, p->ncol, p->inmask.as<uint8_t>(),
+                                                                      p->level.as<int32_t>(), p->receiver.as<int32_t>(), flag.as<int32_t>(),
+                                                                      slot.as<int32_t>(), p->segs.as<SegDesc>(),
+                                                                      cnt.as<unsigned long long>());
+    SCK(cudaGetLastError());
+    gr2m_count_launch(), k_seg_offsets<<<ceil_div(L + 1, 256), 256, 0, st>>>(p->level_off.as<int32_t>(), begin, L, slot.as<int32_t>(),
+                                                                        segoff.as<int32_t>());
+    SCK(cudaGetLastError());
+    p->h_seg_off.assign((size_t)L + 1, 0);
+    unsigned long long ncells = 0;
+    SCK(cudaMemcpyAsync(p->h_seg_off.data() + 1, segoff.as<int32_t>() + 1, (size_t)L * 4, cudaMemcpyDeviceToHost, st));
+    SCK(cudaMemcpyAsync(&ncells, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    cleanup();
+#undef SCK
+#undef SRC
+    if ((long long)ncells != (long long)n || p->h_seg_off[L] != nseg) {      // every cell of the levels in exactly one segment
+        p->segs.release();
+        return GR2M_OK;
+    }
+    p->seg_levels = L;
+    p->nseg = nseg;
+    p->nseg_cells = (long long)ncells;
+    p->seg_ok = true;
+    return GR2M_OK;
+}
+
 static int plan_create_common(const int16_t *flowdir, bool on_device, int nrow, int ncol, int flags, wfa_plan **out)
 {
     REQUIRE(out != nullptr, "out is NULL");
@@ -1638,6 +1879,16 @@ extern "C" int wfa_plan_reach_info(const wfa_plan *p, int *nreaches, int *nreach
     return GR2M_OK;
 }
 
+extern "C" int wfa_plan_segment_info(const wfa_plan *p, long long *nsegments, long long *ncells, int *levels, int *enabled)
+{
+    REQUIRE(p != nullptr, "plan is NULL");
+    if (nsegments) *nsegments = p->seg_ok ? p->nseg : 0;
+    if (ncells) *ncells = p->seg_ok ? p->nseg_cells : 0;
+    if (levels) *levels = p->seg_ok ? p->seg_levels : 0;
+    if (enabled) *enabled = p->seg_ok ? 1 : 0;
+    return GR2M_OK;
+}
+
 extern "C" int wfa_plan_export(const wfa_plan *pc, int32_t *receiver, uint8_t *inmask, int32_t *indeg, int32_t *level,
                                int32_t *order, int32_t *level_off, uint8_t *contam)
 {
@@ -1715,7 +1966,16 @@ static int sweep_g(wfa_plan *p, int nmonth, int ld, T *A, int flags)
         cfg.stream = st;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        const bool by_seg = p->seg_ok && (by_reach || by_basin) && l0 == p->seg_levels && !(flags & WFA_NO_SEGMENTS);
         for (int l = 1; l < l0; ++l) {
+            if (by_seg) {      // chain segments headed at this level (absorbed cells of later levels ride along)
+                const int b = p->h_seg_off[l], e = l + 1 < l0 ? p->h_seg_off[l + 1] : (int)p->nseg;
+                if (e <= b) continue;
+                cfg.gridDim = dim3(ceil_div(e - b, gpb));
+                gr2m_count_launch();
+                CK(cudaLaunchKernelEx(&cfg, k_accum_segments<T, G>, (const SegDesc *)p->segs.as<SegDesc>(), b, e, p->ncol, A, ld, nmonth));
+                continue;
+            }
             int b = off[l], e = off[l + 1];
             cfg.gridDim = dim3(ceil_div(ceil_div(e - b, 2), gpb));
             gr2m_count_launch();

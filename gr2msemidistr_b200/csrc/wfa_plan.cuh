@@ -26,4 +26,10 @@ struct wfa_plan {
     DevBuf rcell, rup_off, rup_idx, run_start, row_off, rowcell, rstream, rinfo, rdone;
     int nrows = 0;
     std::vector<int32_t> h_rlv_off;      // first reach of every reach level
+    // chain segments of the levels below the cut (see k_accum_segments)
+    bool seg_ok = false;
+    int seg_levels = 0;                  // segments cover levels [1, seg_levels)
+    long long nseg = 0, nseg_cells = 0;
+    DevBuf segs;                         // SegDesc[nseg], heads in (level, cell) order
+    std::vector<int32_t> h_seg_off;      // first segment of every level
 };

@@ -62,6 +62,7 @@ extern "C" {
 #define WFA_ROUTE_DENSE       64   /* wfa_route: sweep the whole grid month by month (as AreaD8 does) instead of
                                       applying the month-invariant routing operator, the default */
 #define WFA_NO_OVERLAP       128   /* launch the wide levels without programmatic stream serialization */
+#define WFA_NO_SEGMENTS      256   /* sweep the levels below the cut cell by cell instead of by chain segment (A/B switch) */
 #define WFA_NO_FORWARD        16   /* per-basin sweep without shared-memory forwarding of fresh rows (A/B switch) */
 
 typedef struct gr2m_basin gr2m_basin;   /* forcing + static subbasin data resident in HBM */
@@ -159,6 +160,9 @@ int wfa_plan_basin_info(const wfa_plan *p, int *cut_level, int *nbasins, int *nu
  * group per reach, reaches grouped into `nreach_levels` dependency levels (one launch each);
  * `critical_cells` = sum over those levels of the longest reach, the sweep's serial chain in cells. */
 int wfa_plan_reach_info(const wfa_plan *p, int *nreaches, int *nreach_levels, int *critical_cells, int *enabled);
+/* chain segments of the levels below the cut (csrc/wfa.cu, k_accum_segments): segments, cells they cover, first level
+ * not covered, and whether the default sweep uses them */
+int wfa_plan_segment_info(const wfa_plan *p, long long *nsegments, long long *ncells, int *levels, int *enabled);
 /* Copy the integer topology back (any pointer may be NULL): receiver/indeg/level [ncell] int32,
  * inmask/contam [ncell] uint8, order [norder], level_off [nlevels+1]. */
 int wfa_plan_export(const wfa_plan *p, int32_t *receiver, uint8_t *inmask, int32_t *indeg,

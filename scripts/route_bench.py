@@ -9,15 +9,28 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=8000)
 ap.add_argument("--batches", default="16,32")
 ap.add_argument("--flags", default="0,128")
+ap.add_argument("--terrain", default="tilted", choices=["tilted", "filled"])
 a = ap.parse_args()
 g.build(); capi.set_device(0)
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev); torch.cuda.set_stream(st)
-d8 = synth.d8_grid(a.n, a.n, device=dev); torch.cuda.synchronize()
+if a.terrain == "filled":
+    z, valid = synth.fractal_dem(a.n, a.n, device=dev)
+    v8 = valid.to(torch.uint8).contiguous(); del valid
+    d8 = torch.empty((a.n, a.n), dtype=torch.int16, device=dev)
+    capi.flowdir_from_dem_dev(z.data_ptr(), v8.data_ptr(), a.n, a.n, d8.data_ptr())
+    del z, v8
+else:
+    d8 = synth.d8_grid(a.n, a.n, device=dev)
+torch.cuda.synchronize()
 t0 = time.perf_counter(); plan = capi.Plan(dev_ptr=d8.data_ptr(), shape=(a.n, a.n)); t_plan = time.perf_counter() - t0
 del d8
 plan.set_stream(st.cuda_stream)
-print(json.dumps({"n": a.n, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan, "basins": plan.basin_info(), "reaches": plan.reach_info()}), flush=True)
+import numpy as np, ctypes as C
+lo = np.empty(plan.nlevels + 1, np.int32)
+capi._check(capi.lib().wfa_plan_export(plan._h, None, None, None, None, None, lo.ctypes.data_as(C.POINTER(C.c_int32)), None))
+widths = [int(lo[i + 1] - lo[i]) for i in range(len(lo) - 1)]
+print(json.dumps({"n": a.n, "terrain": a.terrain, "widths_at": {str(k): widths[k] for k in (0, 1, 2, 5, 10, 20, 50, 100, 150, 200, 250, 300, 400, 500, 600, 800, 1000, 2000) if k < len(widths)}, "levels": plan.nlevels, "norder": plan.norder, "plan_s": t_plan, "basins": plan.basin_info(), "reaches": plan.reach_info(), "segments": plan.segment_info()}), flush=True)
 for ld in [int(x) for x in a.batches.split(",")]:
     A = torch.empty((a.n * a.n, ld), dtype=torch.float64, device=dev)
     for fl in [int(x) for x in a.flags.split(",")]:

@@ -224,3 +224,37 @@ def test_linearity_and_mass_conservation_large(capi, rng):
     valid = (pl["level"] >= 0).reshape(nrow, ncol)
     for m in range(nm):
         assert A1[m][term].sum() == W1[m][valid].sum()
+
+
+@pytest.mark.parametrize("terrain,width", [("tilted", 0), ("tilted", 64), ("fractal", 256), ("fractal", 0)])
+def test_chain_segments_are_used_and_bit_identical(capi, oracle, rng, terrain, width, monkeypatch):
+    # default sweep below the cut: a lane group computes a head cell and carries the running sum through the cells
+    # that have no other non-source inflow (csrc/wfa.cu, k_accum_segments).  Same k-ordered additions => same bits
+    # as the cell-by-cell level sweep, as grid-wide level sync and as the CPU oracle; FP64 and float32, any month count.
+    import torch
+    if width:
+        monkeypatch.setenv("WFA_COMP_WIDTH", str(width))
+    nrow, ncol = 640, 900
+    if terrain == "tilted":
+        d = synth.d8_grid(nrow, ncol, seed=13).numpy()
+    else:      # smooth sheet flow with filled depressions: few sources, long single-inflow chains, flats
+        z, valid = synth.fractal_dem(nrow, ncol, relief=4.0)
+        d = capi.flowdir_from_dem(z.numpy(), valid.numpy())
+    NC = capi.WFA_NO_CONTAMINATION
+    with capi.Plan(d) as p:
+        si = p.segment_info()
+        if width:                    # many levels below the cut: the segments must really absorb cells
+            assert si["enabled"] and si["levels"] > 9 and si["ncells"] > 1.15 * si["nsegments"] > 0
+        for nm, fl in ((33, 0), (32, 0), (7, 0), (1, 0), (70, 0), (20, capi.WFA_F32), (40, capi.WFA_F32)):
+            W = rng.uniform(0, 100, (nm, nrow, ncol))
+            A = p.accumulate(W, NC | fl)
+            B = p.accumulate(W, NC | fl | capi.WFA_NO_SEGMENTS)
+            Cc = p.accumulate(W, NC | fl | capi.WFA_LEVEL_SYNC)
+            assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(B, nan=-1)), (nm, fl)
+            assert np.array_equal(np.nan_to_num(A, nan=-1), np.nan_to_num(Cc, nan=-1)), (nm, fl)
+        W = rng.uniform(0, 100, (2, nrow, ncol))
+        A = p.accumulate(W, 0)
+        A32 = p.accumulate(W, capi.WFA_F32)
+        for m in range(2):
+            assert np.array_equal(np.nan_to_num(A[m], nan=-1), np.nan_to_num(oracle.aread8(d, W[m], contcheck=True), nan=-1))
+            assert np.array_equal(np.nan_to_num(A32[m], nan=-1), np.nan_to_num(oracle.aread8(d, W[m], f32=True, contcheck=True), nan=-1))
