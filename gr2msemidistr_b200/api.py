@@ -188,8 +188,9 @@ class _Objective:
     """OFUN of Optim:125-217 with the forcing resident on the GPU; evaluates many sets per call."""
 
     def __init__(self, be, P, E, area, ndays, rid, nreg, qobs, WarmUp, Optimization, fixed_idx, fixed_val, npar,
-                 flags=0):
+                 flags=0, routed=None):
         self.b = be.Basin(P, E, area, ndays, rid, nreg)
+        self.routed = routed               # (plan, router, gauge index): score the routed discharge of one polygon
         self.qobs, self.warmup = qobs, int(WarmUp or 0)
         self.which = _capi.OF_NAMES[Optimization]
         self.fixed_idx, self.fixed_val, self.npar, self.flags = fixed_idx, fixed_val, npar, flags
@@ -207,17 +208,27 @@ class _Objective:
     def __call__(self, X):
         X = np.atleast_2d(np.asarray(X, np.float64))
         self.calls += X.shape[0]
+        if self.routed is not None:
+            return self.b.objective_routed_batch(self.routed[1], self.full(X), self.qobs, self.routed[2], self.warmup,
+                                                 self.which, self.flags, want_crit=False)["of"]
         return self.b.objective_batch(self.full(X), self.qobs, self.warmup, self.which, self.flags,
                                       want_crit=False)["of"]
 
     def close(self):
         self.b.close()
+        if self.routed is not None:
+            self.routed[1].close()
+            self.routed[0].close()
 
 
 def Optim_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters=None, Parameters_Min=None,
                         Parameters_Max=None, Max_Functions=5000, Optimization="NSE", No_Optim=None,
-                        ngs=5, restarts=8, seed=0, flags=0, shard=None):
+                        ngs=5, restarts=8, seed=0, flags=0, shard=None, Gauge=None, Dem=None, FlowDir=None):
     """SCE-UA calibration.  Returns dict(Param, Value) rounded as Optim:232-244.
+
+    `Gauge` (a COMID) switches the objective from the outlet sum of all subbasins (the reference's OFUN) to the ROUTED
+    discharge of that subbasin's polygon: every candidate is simulated, routed over `Dem` (or the given `FlowDir`) by the
+    month-invariant operator and scored there -- Run -> Routing -> hydroGOF in one device call per batch.
 
     `Max_Functions` and `ngs` mean what they mean to rtop::sceua in the reference (evaluation budget and number
     of complexes of ONE search; ngs = 5 is rtop's default).  The GPU batch is filled by `restarts` independent
@@ -251,8 +262,22 @@ def Optim_GR2MSemiDistr(Data, Subbasins, RunIni, RunEnd, WarmUp=None, Parameters
     x0 = Parameters[~fixed]
     if lower.size != x0.size or upper.size != x0.size:
         raise ValueError("Parameters.Min / Parameters.Max must hold 4 values (X1, X2, fp, fpe)")
+    routed = None
+    if Gauge is not None:
+        if Dem is None:
+            raise ValueError("Gauge needs Dem (and optionally FlowDir) to route the simulated discharge")
+        if FlowDir is None:
+            z = np.asarray(Dem.data[0], np.float64)
+            valid = np.isfinite(z) & (z > -1e30)
+            if Dem.nodata is not None:
+                valid &= ~np.isclose(z, Dem.nodata, rtol=1e-6)
+            FlowDir = be.flowdir_from_dem(z, valid)
+        src, off, cells = routing_geometry(Subbasins, Dem)
+        gauge = int(np.flatnonzero(np.asarray(Subbasins.COMID) == Gauge)[0])
+        plan = be.Plan(FlowDir)
+        routed = (plan, plan.router(src, off, cells), gauge)
     obj = _Objective(be, P, E, area, ndays, rid, nreg, qobs, WarmUp, Optimization, np.flatnonzero(fixed),
-                     Parameters[fixed], 4 * nreg, flags)
+                     Parameters[fixed], 4 * nreg, flags, routed)
     print(f"Optimizing {Optimization} with SCE-UA")             # Optim:223
     try:
         res = sceua_batched(obj, x0, lower, upper, maxn=Max_Functions, ngs=ngs, restarts=restarts, seed=seed, shard=shard)

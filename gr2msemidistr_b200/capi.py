@@ -26,7 +26,7 @@ OF_NAMES = {"KGE": OF_KGE, "NSE": OF_NSE, "RMSE": OF_RMSE}
 SYMBOLS = (
     "gr2m_last_error", "gr2m_version", "gr2m_device_count", "gr2m_release_cached_memory", "gr2m_set_device", "gr2m_kernel_launches", "gr2m_guard_checked", "gr2m_guard_violations", "gr2m_fp64_peak",
     "gr2m_basin_create", "gr2m_basin_create_dev", "gr2m_basin_destroy", "gr2m_basin_set_stream", "gr2m_run", "gr2m_run_once",
-    "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_basin_last_kernel_ms",
+    "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_objective_routed_batch", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_plan_segment_info", "wfa_router_create", "wfa_router_destroy",
     "wfa_router_info", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
@@ -187,6 +187,22 @@ class Basin:
         qt = np.empty((nsets, self.ntime)) if want_qt else None
         _check(lib().gr2m_objective_batch(self._h, _dp(params), C.c_int(nsets), _dp(qobs), C.c_int(warmup or 0),
                                           C.c_int(which), C.c_int(flags), _dp(of), _dp(crit), _dp(qt)))
+        return dict(of=of, crit=crit, qt=qt)
+
+    def objective_routed_batch(self, router, params, qobs, gauge: int, warmup: int = 0, which: int = OF_NSE, flags: int = 0,
+                               want_crit: bool = True, want_qt: bool = False):
+        """Run -> Routing -> hydroGOF for many parameter sets: the objective on the ROUTED discharge of polygon `gauge`
+        (0-based index into the router's subbasins).  Returns dict(of, crit, qt) like objective_batch."""
+        params = _f64(params)
+        if params.ndim != 2 or params.shape[1] != 4 * self.nreg:
+            raise ValueError(f"params must be [nsets, {4 * self.nreg}]")
+        nsets = params.shape[0]
+        qobs = _f64(qobs)
+        of = np.full(nsets, np.nan)
+        crit = np.full((nsets, 3), np.nan) if want_crit else None
+        qt = np.empty((nsets, self.ntime)) if want_qt else None
+        _check(lib().gr2m_objective_routed_batch(self._h, router._h, _dp(params), C.c_int(nsets), _dp(qobs), C.c_int(gauge),
+                                                 C.c_int(warmup or 0), C.c_int(which), C.c_int(flags), _dp(of), _dp(crit), _dp(qt)))
         return dict(of=of, crit=crit, qt=qt)
 
     def objective_batch_dev(self, params_ptr: int, nsets: int, qobs, warmup: int, which: int, flags: int,

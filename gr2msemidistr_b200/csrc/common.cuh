@@ -32,6 +32,11 @@ void gr2m_count_launch(void);   // every kernel launch of the library is counted
 int gr2m_check_device(void);   // GR2M_OK, or GR2M_ERR_NODEVICE with the error text set
 int gr2m_current_device(void);
 
+struct wfa_router;
+int wfa_router_nsub(const wfa_router *r);      // router.cu
+int wfa_router_is_f32(const wfa_router *r);
+int wfa_router_wait(wfa_router *r);
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Device memory goes through a small per-process cache of freed blocks (gr2m.cu): handles are created and

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <atomic>
 #include <future>
 #include <mutex>
@@ -556,6 +557,10 @@ struct SimArgs {
     double *out[5];     // PR, AE, SM, RU, QS, each [ncell][ntime] = R's column-major [ntime x ncell]; NULL = not wanted
     double *S_end, *R_end;
     int ncell, ncell_pad, ntime, ntime_pad, nreg, f32exp, forcing_ok;
+    // many parameter sets in one launch (blockIdx.y = set): parameters `param_stride` doubles apart, a set's series
+    // `set_col` columns apart in rows of `pitch` doubles; round_qs: QS rounded like Run:231-235 (R's round(, 1))
+    long long pitch;
+    int param_stride, set_col, round_qs;
 };
 
 // Simulation-mode recursion: one parameter vector, every series written (Run:223-229) -- straight into R's
@@ -576,9 +581,11 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
     if (cell >= a.ncell_pad) return;
     const bool ok = cell < a.ncell;
     const int tl = cell >> 5, lane = cell & 31;
-    CellPar p = load_par(a.params, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0, a.forcing_ok);
+    CellPar p = load_par(a.params + (size_t)blockIdx.y * a.param_stride, a.nreg, ok ? a.region[cell] : 0, ok ? a.area[cell] : 0.0,
+                         a.forcing_ok);
     double S = (a.S0 && ok) ? a.S0[cell] : 0.3 * p.X1;
     double R = (a.R0 && ok) ? a.R0[cell] : 0.5 * p.X2;
+    const size_t col0 = (size_t)blockIdx.y * a.set_col;
     const double *__restrict__ f = a.F + (size_t)tl * a.ntime_pad * 64 + lane;
     const double *__restrict__ den = a.den;
     // the recursion is one dependent chain per thread: keep the forcing of the next U months in flight so a
@@ -615,7 +622,8 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
                     w[32 * SIM_LD] = o.AE;
                     w[2 * 32 * SIM_LD] = S;
                     w[3 * 32 * SIM_LD] = o.Q;
-                    w[4 * 32 * SIM_LD] = (p.area * o.Q) / Dc_[u];
+                    const double qs = (p.area * o.Q) / Dc_[u];
+                    w[4 * 32 * SIM_LD] = a.round_qs ? r_round1(qs, fabs(qs) < 1e8 ? GR2M_TIE_THR : -1.0) : qs;
                 }
             }
         }
@@ -631,15 +639,24 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
 #pragma unroll 4
             for (int r = sub; r < 32; r += 32 / SIM_MB) {
                 const int c = cell0 + r;
-                if (c < a.ncell && mo < nm) __stcs(dst + (size_t)c * a.ntime + tb + mo, src[r * SIM_LD + mo]);
+                if (c < a.ncell && mo < nm) __stcs(dst + (size_t)c * a.pitch + col0 + tb + mo, src[r * SIM_LD + mo]);
             }
         }
         __syncwarp();
     }
-    if (ok) {
+    if (ok && gridDim.y == 1) {
         if (a.S_end) a.S_end[cell] = S;
         if (a.R_end) a.R_end[cell] = R;
     }
+}
+
+// gauge row of the routed discharge -> [set][month], rounded like Routing:131 (R's round(, 1)) unless told otherwise
+__global__ void k_gauge_row(const double *__restrict__ row, long long n, int round1, double *__restrict__ out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = row[i];
+    out[i] = round1 ? r_round1(v, fabs(v) < 1e8 ? GR2M_TIE_THR : -1.0) : v;
 }
 
 struct ObjArgs {
@@ -926,6 +943,7 @@ extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, c
     a.S_end = b->send.as<double>(); a.R_end = b->rend.as<double>();
     a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad;
     a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
+    a.pitch = b->ntime; a.param_stride = 0; a.set_col = 0; a.round_qs = 0;
     const size_t smem = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * sizeof(double);
     auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -956,27 +974,31 @@ extern "C" int gr2m_run_once(int ntime, int ncell, const double *P, const double
     return rc;
 }
 
+// qobs -> device (cached: re-uploaded only when the host values change)
+static int upload_qobs(gr2m_basin *b, const double *qobs)
+{
+    if (!qobs) return GR2M_OK;
+    int rc;
+    bool same = b->qobs_host_copy && b->qobs_n == b->ntime && memcmp(b->qobs_host_copy, qobs, b->ntime * sizeof(double)) == 0;
+    if (!same) {
+        if ((rc = b->qobs.ensure(b->ntime * sizeof(double)))) return rc;
+        free(b->qobs_host_copy);
+        b->qobs_host_copy = (double *)malloc(b->ntime * sizeof(double));
+        if (!b->qobs_host_copy) { gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
+        memcpy(b->qobs_host_copy, qobs, b->ntime * sizeof(double));
+        b->qobs_n = b->ntime;
+        CK(cudaMemcpyAsync(b->qobs.p, b->qobs_host_copy, b->ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    }
+    return GR2M_OK;
+}
+
 static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, const double *qobs, int warmup,
                             int which, int flags, double *of_dev, double *crit_dev, double *qt_dev)
 {
     int rc;
     if (!b->sm_count) CK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
-    // qobs -> device (cached: re-uploaded only when the host values change)
     const bool has_obs = qobs != nullptr;
-    if (has_obs) {
-        bool same = b->qobs_host_copy && b->qobs_n == b->ntime &&
-                    memcmp(b->qobs_host_copy, qobs, b->ntime * sizeof(double)) == 0;
-        if (!same) {
-            if ((rc = b->qobs.ensure(b->ntime * sizeof(double)))) return rc;
-            free(b->qobs_host_copy);
-            b->qobs_host_copy = (double *)malloc(b->ntime * sizeof(double));
-            if (!b->qobs_host_copy) { gr2m_set_error("host allocation failed"); return GR2M_ERR_NOMEM; }
-            memcpy(b->qobs_host_copy, qobs, b->ntime * sizeof(double));
-            b->qobs_n = b->ntime;
-            CK(cudaMemcpyAsync(b->qobs.p, b->qobs_host_copy, b->ntime * sizeof(double), cudaMemcpyHostToDevice,
-                               b->stream));
-        }
-    }
+    if ((rc = upload_qobs(b, qobs))) return rc;
     const bool fast = !(flags & GR2M_MATH_LITERAL);
     // one region: per-set power tables (gr2m_calib3.cuh); several regions: a lane's X1 depends on its cell
     static const bool no_tab = getenv("GR2M_CALIB_GENERIC") != nullptr;
@@ -1094,6 +1116,86 @@ extern "C" int gr2m_objective_batch(gr2m_basin *b, const double *params, int nse
     if (out_qt)
         CK(cudaMemcpyAsync(out_qt, b->qt.p, (size_t)nsets * b->ntime * sizeof(double), cudaMemcpyDeviceToHost,
                            b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return GR2M_OK;
+}
+
+// Routed objective: the reference's Run -> Routing -> hydroGOF chain for many parameter sets at once.  Every set is
+// simulated for every subbasin (QS rounded to 0.1 like Run_GR2MSemiDistr returns it, Run:229-235), the sets x months
+// become the columns of ONE application of the month-invariant routing operator (wfa_router, Routing:100-123), the
+// routed discharge at the gauge polygon (rounded to 0.1, Routing:131) is scored against qobs (Optim:199-212).
+// GR2M_SINK_UNROUNDED skips both roundings.  Sets are processed in chunks of <= ~1 GB of QS.
+extern "C" int gr2m_objective_routed_batch(gr2m_basin *b, wfa_router *r, const double *params, int nsets, const double *qobs,
+                                           int gauge, int warmup, int which, int flags, double *out_of, double *out_crit,
+                                           double *out_qt)
+{
+    REQUIRE(b && r && params, "NULL handle, router or params");
+    REQUIRE(nsets > 0, "nsets must be positive");
+    REQUIRE(which >= 0 && which <= 2, "which must be GR2M_OF_KGE, _NSE or _RMSE");
+    REQUIRE(warmup < b->ntime, "warmup must be smaller than ntime");
+    REQUIRE(qobs || out_qt, "nothing to compute: qobs and out_qt are both NULL");
+    REQUIRE(wfa_router_nsub(r) == b->ncell, "the router was built for a different number of subbasins");
+    REQUIRE(!wfa_router_is_f32(r), "the routed objective needs an FP64 router");
+    REQUIRE(gauge >= 0 && gauge < b->ncell, "gauge polygon index out of range");
+    CK(cudaSetDevice(b->device));
+    if (!b->sm_count) CK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
+    int rc;
+    const int nt = b->ntime;
+    const size_t np = (size_t)nsets * 4 * b->nreg;
+    if ((rc = b->params.ensure(np * sizeof(double)))) return rc;
+    if ((rc = b->of.ensure(nsets * sizeof(double)))) return rc;
+    if ((rc = b->crit.ensure((size_t)nsets * 3 * sizeof(double)))) return rc;
+    if ((rc = b->qt.ensure((size_t)nsets * nt * sizeof(double)))) return rc;
+    if ((rc = b->partial.ensure((size_t)nsets * nt * sizeof(double)))) return rc;      // gauge series [set][month]
+    CK(cudaMemcpyAsync(b->params.p, params, np * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    if ((rc = upload_qobs(b, qobs))) return rc;
+    long long per_set = (long long)b->ncell * nt * 8;
+    int chunk = (int)std::min<long long>(nsets, std::max<long long>(1, (1ll << 30) / per_set));
+    DevBuf qs, qr;
+    if ((rc = qs.ensure((size_t)chunk * per_set)) || (rc = qr.ensure((size_t)chunk * per_set))) { qs.release(); qr.release(); return rc; }
+    const bool unr = (flags & GR2M_SINK_UNROUNDED) != 0;
+    const size_t smem = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * sizeof(double);
+    auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CK(cudaEventRecord(b->ev0, b->stream));
+    for (int s0 = 0; s0 < nsets && e == cudaSuccess && !rc; s0 += chunk) {
+        const int cs = std::min(chunk, nsets - s0);
+        SimArgs a;
+        a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = b->params.as<double>() + (size_t)s0 * 4 * b->nreg;
+        a.den = b->den.as<double>(); a.S0 = nullptr; a.R0 = nullptr; a.region = b->region.as<int>();
+        for (int v = 0; v < 4; ++v) a.out[v] = nullptr;
+        a.out[4] = qs.as<double>();
+        a.S_end = nullptr; a.R_end = nullptr;
+        a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = nt; a.ntime_pad = b->ntime_pad; a.nreg = b->nreg;
+        a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
+        a.pitch = (long long)cs * nt; a.param_stride = 4 * b->nreg; a.set_col = nt; a.round_qs = unr ? 0 : 1;
+        gr2m_count_launch(), kern<<<dim3(ceil_div(b->ncell_pad, SIM_WARPS * 32), cs), SIM_WARPS * 32, smem, b->stream>>>(a);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);          // the router works on its plan's stream
+        if (e != cudaSuccess) break;
+        if ((rc = wfa_router_apply_dev(r, cs * nt, qs.as<double>(), qr.as<double>()))) break;
+        if ((rc = wfa_router_wait(r))) break;
+        const long long n = (long long)cs * nt;
+        gr2m_count_launch(), k_gauge_row<<<ceil_div(n, 256), 256, 0, b->stream>>>(qr.as<double>() + (size_t)gauge * cs * nt, n, unr ? 0 : 1,
+                                                                             b->partial.as<double>() + (size_t)s0 * nt);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(b->stream);
+    qs.release(); qr.release();
+    if (rc) return rc;
+    if (e != cudaSuccess) { gr2m_set_error("gr2m_objective_routed_batch: %s", cudaGetErrorString(e)); cudaGetLastError(); return GR2M_ERR_CUDA; }
+    ObjArgs o;
+    o.partial = b->partial.as<double>(); o.qobs = qobs ? b->qobs.as<double>() : nullptr;
+    o.qt = b->qt.as<double>(); o.of = b->of.as<double>(); o.crit = b->crit.as<double>();
+    o.csplit = 1; o.nsets = nsets; o.ntime = nt; o.warmup = warmup < 0 ? 0 : warmup; o.which = which;
+    o.single_cell = 0; o.unrounded = 1; o.has_obs = qobs != nullptr;       // the series is already rounded the reference's way
+    gr2m_count_launch(), k_objective<<<ceil_div((long long)nsets * 32, 128), 128, 0, b->stream>>>(o);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, b->stream));
+    b->timed = true;
+    if (out_of && qobs) CK(cudaMemcpyAsync(out_of, b->of.p, nsets * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (out_crit && qobs) CK(cudaMemcpyAsync(out_crit, b->crit.p, (size_t)nsets * 3 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (out_qt) CK(cudaMemcpyAsync(out_qt, b->qt.p, (size_t)nsets * nt * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return GR2M_OK;
 }

@@ -526,6 +526,17 @@ extern "C" int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_d
                                 : router_apply_t<double>(r, ncols, QS_dev, QR_dev);
 }
 
+// for gr2m_objective_routed_batch (gr2m.cu): number of subbasins, and "wait until the last apply is done"
+int wfa_router_nsub(const wfa_router *r) { return r ? r->nsub : -1; }
+int wfa_router_is_f32(const wfa_router *r) { return r && (r->flags & WFA_F32) ? 1 : 0; }
+int wfa_router_wait(wfa_router *r)
+{
+    REQUIRE(r != nullptr, "router is NULL");
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->plan->stream));
+    return GR2M_OK;
+}
+
 extern "C" int wfa_router_apply(wfa_router *r, int ncols, const double *QS, double *QR)
 {
     REQUIRE(r && QS && QR, "NULL argument");

@@ -191,7 +191,17 @@ void wfa_router_destroy(wfa_router *r);
  * length of the per-polygon node lists; nactive: grid cells at or below a source. */
 int wfa_router_info(const wfa_router *r, int *nnodes, int *nlevels, int *ncandidates, long long *nactive);
 int wfa_router_apply(wfa_router *r, int ncols, const double *QS, double *QR);           /* host buffers */
-int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_dev, double *QR_dev); /* device, async */
+int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_dev, double *QR_dev);
+
+/* Routed objective (north_star's simulate + route + objective loop): the reference's chain Run_GR2MSemiDistr ->
+ * Routing_GR2MSemiDistr -> hydroGOF for nsets parameter sets at once.  Per set: QS of every subbasin rounded to 0.1
+ * (Run:229-235), routed by the operator (Routing:100-123; months x sets are its columns), QR of polygon `gauge`
+ * (0-based) rounded to 0.1 (Routing:131), scored against qobs as in Optim:199-212.  GR2M_SINK_UNROUNDED skips both
+ * roundings.  Outputs as gr2m_objective_batch (out_qt: the gauge series, [nsets][ntime]).  The router must be FP64 and
+ * built for the basin's subbasins in the same order. */
+int gr2m_objective_routed_batch(gr2m_basin *b, wfa_router *r, const double *params, int nsets, const double *qobs,
+                                int gauge, int warmup, int which, int flags, double *out_of, double *out_crit,
+                                double *out_qt); /* device, async */
 
 /* Dense AreaD8 -wg for nmonth weight grids: W, A are [nmonth][ncell] (month planes, row-major
  * cells).  Nodata / contaminated cells come back as NaN (TauDEM -1 -> NA after raster()). */

@@ -119,3 +119,20 @@ def test_calibration_on_the_gpu(capi, c1, monkeypatch):
                      Parameters_Max=[2000, 2, 1.2, 1.2], Max_Functions=3000, Optimization="KGE", restarts=2)
     assert res["Value"] >= ref["Value"] - 0.005 and res["Value"] > 0.5
     assert res["evaluations"] > 223 * 1000
+
+
+def test_routed_calibration_through_the_wrapper(capi, c1):
+    # Optim_GR2MSemiDistr(..., Gauge=<COMID>): SCE-UA on the ROUTED discharge of that subbasin's polygon
+    inp, _ = c1
+    data, sb = _frame(inp), _subbasins(inp)
+    dem = gis.Raster(np.where(inp["dem"] == -32768, -3e38, inp["dem"]).astype(np.float32)[None], *inp["dem_geo"], nodata=-3e38)
+    with capi.Plan(inp["flowdir"]) as plan:
+        QR = plan.route(inp["P"][:, :24] * 0 + 1.0, inp["src_cell"], inp["poly_off"], inp["poly_cells"])
+    outlet = int(np.argmax(np.where(np.isfinite(QR[:, 0]), QR[:, 0], -1)))          # routes a unit discharge from everyone
+    assert QR[outlet, 0] == 13.0                                                     # ... and one polygon sees all 13
+    kw = dict(WarmUp=36, Parameters=[1000, 1, 1, 1], Parameters_Min=[1, 0.01, 0.8, 0.8], Parameters_Max=[2000, 2, 1.2, 1.2],
+              Max_Functions=600, Optimization="KGE", restarts=4)
+    res = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", Gauge=int(sb.COMID[outlet]), Dem=dem, FlowDir=inp["flowdir"], **kw)
+    ref = api.Optim_GR2MSemiDistr(data, sb, "01/1981", "12/2002", **kw)
+    # at the basin outlet the routed series is the outlet sum up to rounding to 0.1: the two calibrations land together
+    assert res["Value"] > 0.5 and abs(res["Value"] - ref["Value"]) < 0.05
