@@ -1,4 +1,5 @@
-# GR2MSemiDistr front end over libgr2m_b200.so -- UNTESTED (no R in the build image).
+# GR2MSemiDistr front end over libgr2m_b200.so.  Never run under R (no R in the build image): the .Call glue it uses is compiled and
+# executed against a mock R API (tests/test_r_shim.py); the R code itself is checked there for routine names / argument counts.
 # Exported signatures and return structures follow GR2MSemiDistr 4.2.1
 # (R/Run_GR2MSemiDistr.R:48, R/Optim_GR2MSemiDistr.R:41, R/Routing_GR2MSemiDistr.R:35);
 # the arithmetic is done by .Call into the C ABI, the wrappers keep only what must stay in R:
@@ -71,9 +72,27 @@ gr2m_objective_batch <- function(handle, parameter_sets, Qobs, WarmUp = 0L,
         as.integer(WarmUp), which, .gr2m_flags())
 }
 
+# Month-invariant inputs of the routing seam (Routing:77-81, 119-121), shared by Routing_ and the routed calibration
+.gr2m_routing_geometry <- function(Subbasins, Dem, FlowDir) {
+  roi  <- sf::st_as_sf(Subbasins)
+  cen  <- methods::as(sf::st_as_sf(geos::geos_point_on_surface(roi)), "Spatial")
+  src  <- raster::cellFromXY(Dem, sp::coordinates(cen)) - 1L        # 0-based row-major
+  cov  <- exactextractr::exact_extract(Dem, roi, include_cell = TRUE, progress = FALSE)
+  inner <- lapply(cov, function(d) d$cell[d$coverage_fraction == 1] - 1L)
+  if (is.null(FlowDir)) {           # no TauDEM: pit filling + D8 codes on the GPU (own flat rule, see DESIGN.md)
+    fd <- .Call(C_wfa_flowdir, raster::as.matrix(Dem) * 1.0)
+  } else {                          # FlowDir.tif of "D8Flowdir -p" as a RasterLayer
+    fd <- raster::as.matrix(FlowDir); storage.mode(fd) <- "integer"
+  }
+  list(fd = fd, src = as.integer(src), off = as.integer(c(0, cumsum(lengths(inner)))), cells = as.integer(unlist(inner)),
+       comid = as.vector(roi$COMID))
+}
+
+# Gauge / Dem / FlowDir are additions after the reference's arguments: with Gauge (a COMID) every candidate is
+# simulated, routed over the DEM and scored on the routed discharge of that subbasin's polygon in one device call.
 Optim_GR2MSemiDistr <- function(Data, Subbasins, RunIni, RunEnd, WarmUp = NULL, Parameters,
                                 Parameters.Min, Parameters.Max, Max.Functions = 5000,
-                                Optimization = "NSE", No.Optim = NULL) {
+                                Optimization = "NSE", No.Optim = NULL, Gauge = NULL, Dem = NULL, FlowDir = NULL) {
   tictoc::tic()
   s <- .gr2m_setup(Data, Subbasins, RunIni, RunEnd)
   nreg  <- length(s$zone)
@@ -82,9 +101,17 @@ Optim_GR2MSemiDistr <- function(Data, Subbasins, RunIni, RunEnd, WarmUp = NULL, 
   nopt  <- nreg - sum(s$zone %in% No.Optim)
   h <- .Call(C_gr2m_basin, s$P, s$E, s$area, s$ndays, s$region_id, nreg)
   warm <- if (is.null(WarmUp)) 0L else as.integer(WarmUp)
+  routing <- NULL; gauge <- 0L
+  if (!is.null(Gauge)) {
+    g <- .gr2m_routing_geometry(Subbasins, Dem, FlowDir)
+    routing <- .Call(C_wfa_router, g$fd, g$src, g$off, g$cells)
+    gauge <- match(Gauge, g$comid) - 1L
+  }
+  which <- match(Optimization, c("KGE", "NSE", "RMSE")) - 1L
   OFUN <- function(parameter_set) {            # drop-in body: one candidate, forcing already on the GPU
     full <- as.numeric(Parameters); full[!fixed] <- parameter_set
-    gr2m_objective_batch(h, matrix(full, ncol = 1), s$Q, warm, Optimization)
+    if (is.null(routing)) gr2m_objective_batch(h, matrix(full, ncol = 1), s$Q, warm, Optimization)
+    else .Call(C_gr2m_objective_routed, h, routing, matrix(full, ncol = 1), as.numeric(s$Q), gauge, warm, which, .gr2m_flags())
   }
   message(paste("Optimizing", Optimization, "with SCE-UA"))
   cal <- rtop::sceua(OFUN, pars = Parameters[!fixed], lower = rep(Parameters.Min, each = nopt),
@@ -107,20 +134,10 @@ Routing_GR2MSemiDistr <- function(Model, Subbasins, Dem, AcumIni = NULL, AcumEnd
     i <- seq(which(k == paste0("01/", AcumIni)), which(k == paste0("01/", AcumEnd)))
     QS <- QS[i, , drop = FALSE]; Dates <- Dates[i]
   }
-  roi  <- sf::st_as_sf(Subbasins)
-  cen  <- methods::as(sf::st_as_sf(geos::geos_point_on_surface(roi)), "Spatial")
-  src  <- raster::cellFromXY(Dem, sp::coordinates(cen)) - 1L        # 0-based row-major
-  cov  <- exactextractr::exact_extract(Dem, roi, include_cell = TRUE, progress = FALSE)
-  inner <- lapply(cov, function(d) d$cell[d$coverage_fraction == 1] - 1L)
-  off  <- as.integer(c(0, cumsum(lengths(inner))))
-  if (is.null(FlowDir)) {           # no TauDEM: pit filling + D8 codes on the GPU (own flat rule, see DESIGN.md)
-    fd <- .Call(C_wfa_flowdir, raster::as.matrix(Dem) * 1.0)
-  } else {                          # FlowDir.tif of "D8Flowdir -p" as a RasterLayer
-    fd <- raster::as.matrix(FlowDir); storage.mode(fd) <- "integer"
-  }
+  g <- .gr2m_routing_geometry(Subbasins, Dem, FlowDir)
   message(paste0("Routing streamflows for ", ncol(QS), " sub-basins"))
-  qr <- round(.Call(C_wfa_route, fd, QS * 1.0, as.integer(src), off, as.integer(unlist(inner)), 0L), 1)
-  Ans <- list(QR = qr, Dates = Dates, COMID = as.vector(roi$COMID))
+  qr <- round(.Call(C_wfa_route, g$fd, QS * 1.0, g$src, g$off, g$cells, 0L), 1)
+  Ans <- list(QR = qr, Dates = Dates, COMID = g$comid)
   if (Save) .gr2m_save(c(Ans, list(Dates = Dates)), "QR", format(utils::tail(Dates, 1), "%m/%Y"), Update)
   message("Done!"); tictoc::toc()
   Ans

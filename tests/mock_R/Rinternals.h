@@ -7,6 +7,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -52,6 +53,10 @@ void R_ClearExternalPtr(SEXP s);
 void R_RegisterCFinalizerEx(SEXP s, void (*fun)(SEXP), Rboolean onexit);
 
 /* helpers of the mock itself (used by the test driver) */
+long Rf_xlength(SEXP x);
+#define R_Calloc(n, T) ((T *)calloc((size_t)(n), sizeof(T)))
+#define R_Free(p) (free((void *)(p)), (p) = NULL)
+
 SEXP mock_scalar_int(int v);
 void mock_run_finalizers(void);
 

@@ -30,6 +30,7 @@ double *REAL(SEXP x) { need(x, REALSXP, "REAL()"); return (double *)x->data; }
 int *INTEGER(SEXP x) { need(x, INTSXP, "INTEGER()"); return (int *)x->data; }
 int Rf_nrows(SEXP x) { return x->ncol < 0 ? (int)x->length : x->nrow; }
 int Rf_ncols(SEXP x) { return x->ncol < 0 ? 1 : x->ncol; }
+long Rf_xlength(SEXP x) { return x->length; }
 int Rf_isNull(SEXP x) { return x == R_NilValue || x->type == NILSXP; }
 int Rf_asInteger(SEXP x)
 {

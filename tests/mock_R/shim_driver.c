@@ -70,7 +70,9 @@ static DL_FUNC routine(const char *name, int nargs)
     exit(5);
 }
 typedef SEXP (*F1)(SEXP);
+typedef SEXP (*F4)(SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F6)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 int main(int argc, char **argv)
@@ -78,7 +80,8 @@ int main(int argc, char **argv)
     if (argc < 2) { fprintf(stderr, "usage: shim_driver <dir>\n"); return 1; }
     dir = argv[1];
     size_t b;
-    int *dims = (int *)slurp("dims.bin", &b);      /* ntime ncell nreg nsets warmup which nrow ncol rt_ntime rt_nsub npoly flags */
+    int *dims = (int *)slurp("dims.bin", &b);      /* ntime ncell nreg nsets warmup which nrow ncol rt_ntime rt_nsub npoly flags
+                                                        rt2_nrow rt2_ncol rt2_npoly gauge */
     const int ntime = dims[0], ncell = dims[1], nreg = dims[2], nsets = dims[3], warmup = dims[4], which = dims[5];
     const int nrow = dims[6], ncol = dims[7], rt_ntime = dims[8], rt_nsub = dims[9], npoly = dims[10], flags = dims[11];
     R_init_GR2MSemiDistrB200(&dll);
@@ -110,8 +113,17 @@ int main(int argc, char **argv)
     SEXP params = real_matrix("params.bin", 4 * nreg, nsets), qobs = real_matrix("qobs.bin", ntime, -1);
     SEXP of = ((F6)routine("C_gr2m_objective", 6))(h, params, qobs, mock_scalar_int(warmup), mock_scalar_int(which), mock_scalar_int(flags));
     dump("out_of.bin", REAL(of), (size_t)nsets * 8);
-    mock_run_finalizers();                                   /* gc(): the external pointer's finalizer destroys the handle */
-    if (R_ExternalPtrAddr(h) != NULL) { fprintf(stderr, "finalizer did not clear the handle\n"); return 6; }
+    /* Optim_GR2MSemiDistr(Gauge = ...): routing operator on the run's own subbasins, objective on the routed discharge */
+    {
+        SEXP fd2 = int_array("rt2_flowdir.bin", dims[12], dims[13]), src2 = int_array("rt2_src.bin", ncell, -1);
+        SEXP off2 = int_array("rt2_off.bin", ncell + 1, -1), cells2 = int_array("rt2_cells.bin", dims[14] > 0 ? dims[14] : 1, -1);
+        SEXP rh = ((F4)routine("C_wfa_router", 4))(fd2, src2, off2, cells2);
+        SEXP ofr = ((F8)routine("C_gr2m_objective_routed", 8))(h, rh, params, qobs, mock_scalar_int(dims[15]), mock_scalar_int(warmup),
+                                                               mock_scalar_int(which), mock_scalar_int(flags));
+        dump("out_of_routed.bin", REAL(ofr), (size_t)nsets * 8);
+        mock_run_finalizers();                               /* gc(): the finalizers destroy the basin, the operator and the plan */
+        if (R_ExternalPtrAddr(h) != NULL || R_ExternalPtrAddr(rh) != NULL) { fprintf(stderr, "finalizer did not clear a handle\n"); return 6; }
+    }
 
     /* Routing_GR2MSemiDistr: DEM -> directions, then the routing seam; matrices as raster::as.matrix gives them */
     SEXP dem = real_matrix("dem.bin", nrow, ncol);

@@ -49,7 +49,8 @@ def test_registered_routines_match_the_r_code_and_namespace():
     shim = open(SHIM).read()
     rcode = open(os.path.join(ROOT, "r_package", "R", "gr2m_b200.R")).read()
     table = dict(re.findall(r'\{"(C_\w+)", \(DL_FUNC\)&\1, (\d+)\}', shim))
-    assert set(table) == {"C_gr2m_run", "C_gr2m_basin", "C_gr2m_objective", "C_wfa_route", "C_wfa_flowdir"}
+    assert set(table) == {"C_gr2m_run", "C_gr2m_basin", "C_gr2m_objective", "C_wfa_route", "C_wfa_flowdir", "C_wfa_router",
+                          "C_gr2m_objective_routed"}
     # every .Call in the R code names a registered routine and passes as many arguments as registered
     calls = re.findall(r"\.Call\((C_\w+)((?:[^()]|\([^()]*(?:\([^()]*\)[^()]*)*\))*)\)", rcode)
     assert calls
@@ -104,7 +105,16 @@ def test_shim_outputs_equal_the_ctypes_path(tmp_path):
 
     def put(name, a, dt):
         np.ascontiguousarray(a, dtype=dt).tofile(os.path.join(d, name))
-    put("dims.bin", [ntime, ncell, nreg, nsets, warm, which, nrow, ncol, rt_ntime, rt_nsub, len(cells), flags], np.int32)
+    # a second geometry with one polygon per simulated subbasin, for the routed objective
+    n2r, n2c = 48, 60
+    d8b = synth.d8_grid(n2r, n2c, seed=84).numpy()
+    src2, off2, cells2 = synth.block_polygons(n2r, n2c, 5, 9, margin=1)
+    assert len(src2) == ncell
+    gauge = 31
+    put("dims.bin", [ntime, ncell, nreg, nsets, warm, which, nrow, ncol, rt_ntime, rt_nsub, len(cells), flags,
+                     n2r, n2c, len(cells2), gauge], np.int32)
+    put("rt2_flowdir.bin", np.where(d8b < 1, np.iinfo(np.int32).min, d8b.astype(np.int32)).T, np.int32)   # column-major, NA = INT_MIN
+    put("rt2_src.bin", src2, np.int32); put("rt2_off.bin", off2, np.int32); put("rt2_cells.bin", cells2, np.int32)
     put("P.bin", P, np.float64); put("E.bin", E, np.float64)                 # [ncell, ntime] C order == [ntime x ncell] column-major
     put("area.bin", area, np.float64); put("ndays.bin", nd, np.int32); put("region.bin", region, np.int32)
     put("par0.bin", par[0], np.float64)
@@ -129,6 +139,9 @@ def test_shim_outputs_equal_the_ctypes_path(tmp_path):
     with capi.Basin(P, E, area, nd, region, nreg) as b:
         of = b.objective_batch(par, qobs, warm, which, flags)["of"]
     assert np.array_equal(get("out_of.bin", np.float64, nsets), of, equal_nan=True)
+    with capi.Plan(d8b) as plan2, plan2.router(src2, off2, cells2) as router2, capi.Basin(P, E, area, nd, region, nreg) as b:
+        ofr = b.objective_routed_batch(router2, par, qobs, gauge, warm, which, flags)["of"]
+    assert np.array_equal(get("out_of_routed.bin", np.float64, nsets), ofr, equal_nan=True)
     fd = capi.flowdir_from_dem(np.where(valid, dem, 0.0), valid)
     got_fd = get("out_flowdir.bin", np.int32, (ncol, nrow)).T                  # column-major integer matrix, NA = INT_MIN
     assert np.array_equal(np.where(got_fd == np.iinfo(np.int32).min, -32768, got_fd), fd.astype(np.int32))
