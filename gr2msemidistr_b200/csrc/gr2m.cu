@@ -1016,12 +1016,11 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         tiles_per_split = gps * group_tiles;
         csplit = ngroups;
     } else {
-        // decomposition: nsg set groups x csplit ranges of cell tiles, ~8 waves of 3 blocks/SM
-        const int target = b->sm_count * 4 * 8;
-        csplit = ceil_div(target, nsg);
-        if (csplit > b->ntiles) csplit = b->ntiles;
-        if (csplit < 1) csplit = 1;
-        tiles_per_split = ceil_div(b->ntiles, csplit);
+        // general kernel (several regions, literal arithmetic): one block per set group and canonical group of tiles, the
+        // same grouping rule, so these sums do not depend on the batch size either
+        group_tiles = 4;
+        while (group_tiles * 2 * 32 <= b->ntiles) group_tiles *= 2;
+        tiles_per_split = group_tiles;
         csplit = ceil_div(b->ntiles, tiles_per_split);
     }
     if ((rc = b->partial.ensure((size_t)csplit * nsets * b->ntime * sizeof(double)))) return rc;
