@@ -763,6 +763,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 10: r = exp_tab2048(x[i], g_exp2_tab2048); break;
         case 11: r = 2.0 * exp_idx2048_half(clamp_u26(x[i] * 0x1.71547652b82fep+11), g_exp2_tab2048); break;
         case 12: r = rcbrt_fast_poly(x[i]); break;
+        case 13: r = div_fast3q(x[i], y[i]); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;

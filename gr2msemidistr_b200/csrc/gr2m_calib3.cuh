@@ -57,9 +57,9 @@ template <bool F32EXP>
 __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, double a2, double b2, double &s, double &rho)
 {
     double am = a2 - 0.5, ap = a2 + 0.5;
-    double s1 = div_fast3(__fma_rn(s, ap, am), __fma_rn(s, am, ap));
-    // (b2 + 1/2) + (1 - s1)(b2 - 1/2) = b2 (2 - s1) + s1/2: one FP64 instruction less
-    double s2 = div_fast3(s1, __fma_rn(b2, 2.0 - s1, 0.5 * s1));
+    double s1 = div_fast3q(__fma_rn(s, ap, am), __fma_rn(s, am, ap));
+    // (b2 + 1/2) + (1 - s1)(b2 - 1/2) = 2 b2 + s1 (1/2 - b2): one FP64 instruction less, and only one of them after s1
+    double s2 = div_fast3q(s1, __fma_rn(s1, 0.5 - b2, b2 + b2));
     double c = __fma_rn(s2 * s2, s2, 1.0);
 #if GR2M_WHATIF == 1
     double y = __fma_rn(c, -0.2, 1.0);            // no cube root: -5 FP64, -4 XU, -1 FMUL
@@ -75,7 +75,7 @@ __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, do
 #if GR2M_WHATIF == 5
     double q = rho2 * rho2 * 0.01;               // no third division: -4 FP64, -1 XU, -1 MOV
 #else
-    double q = div_fast3(rho2 * rho2, rho2 + p.kappa);
+    double q = div_fast3q(rho2 * rho2, rho2 + p.kappa);
 #endif
     rho = rho2 - q;
     s = sn;

@@ -2,7 +2,7 @@
 # Round-2 evidence run: default bench, then (only after each plain command exited 0) the ncu passes profiles/ quotes.
 #   gpurun --timeout 2400 -- 'bash scripts/gpu_profile.sh'
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-300
+echo "(default bench: see gpu_check.sh)"
 SMALL="python bench.py --steps 2 --warmup 3 --sets 1250 --cells 20000 --route-n 0 --no-cpu --no-e2e"
 $SMALL > gpurun_out/ncu_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_gr2m_calib -s 3 -c 1 -o gpurun_out/r2_calib4 -f $SMALL > gpurun_out/ncu_c4.log 2>&1; echo "ncu slice rc=$?"
 FULL="python bench.py --steps 1 --warmup 3 --route-n 0 --no-cpu --no-e2e"

@@ -49,6 +49,7 @@ def test_device_math_building_blocks(capi, oracle, rng):
     assert np.max(np.abs(capi.debug_math(3, n, dd) / (n / dd) - 1)) < 4.5e-16
     assert np.max(np.abs(capi.debug_math(6, n, dd) / (n / dd) - 1)) < 4.5e-16      # the one-Newton-step variant in use
     assert np.max(np.abs(capi.debug_math(7, n, dd) / (n / dd) - 1)) < 6e-16        # cubic-step variant (not in use unless it passes here)
+    assert np.max(np.abs(capi.debug_math(13, n, dd) / (n / dd) - 1)) < 6e-16       # same with the numerator multiplied in early (shipped)
     assert np.max(np.abs(capi.debug_math(8, e) / np.exp(e) - 1)) < 7e-16           # 256-entry table, degree 4
     # 2048-entry table, degree 3, one-FMA reduction (shipped calibration step): <= 1.4e-15 at x = 26 by construction
     assert np.max(np.abs(capi.debug_math(10, e) / np.exp(e) - 1)) < 2.5e-15
@@ -280,3 +281,19 @@ def test_objective_degenerate_series_match_oracle(capi, oracle):
     assert np.all(ref["qt"] == 0.0) and np.all(np.isnan(ref["crit"][:, 0])) and np.all(np.isfinite(ref["crit"][:, 1:]))
     ref = oracle.objective_batch(P, E, area, nd, region, 1, par[:2], np.full(ntime, 42.0), wu)
     assert np.all(np.isnan(ref["crit"][:, :2])) and np.all(np.isfinite(ref["crit"][:, 2]))
+
+
+@pytest.mark.parametrize("nreg", [1, 2])
+def test_sums_do_not_depend_on_batch_size_or_rank_count(capi, nreg):
+    # Outlet sums are accumulated per canonical group of cell tiles (a function of the number of cells only), so the
+    # bits of a set's series are the same whether it is evaluated alone, in a batch of 8 or of 640 -- i.e. for any
+    # split of the sets over ranks -- although the launch is cut into very different blocks in each case.
+    ncell, ntime = 9000, 48
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=91)
+    region = (np.arange(ncell) % nreg).astype(np.int32)
+    par = synth.param_sets(640, nreg, seed=92)
+    with capi.Basin(P, E, area, nd, region, nreg) as b:
+        full = b.objective_batch(par, None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
+        for lo, hi in ((0, 1), (5, 13), (100, 260), (633, 640)):
+            part = b.objective_batch(par[lo:hi], None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
+            assert np.array_equal(part, full[lo:hi]), (lo, hi)
