@@ -274,11 +274,12 @@ __global__ void k_seg_flag(const int32_t *__restrict__ order, int begin, int end
 // heads write their descriptor at the slot the scan gave them
 __global__ void k_seg_build(const int32_t *__restrict__ order, int begin, int end, int seg_levels, int ncol,
                             const uint8_t *__restrict__ inmask, const int32_t *__restrict__ level,
-                            const int32_t *__restrict__ receiver, const int32_t *__restrict__ flag,
-                            const int32_t *__restrict__ slot, SegDesc *__restrict__ segs, unsigned long long *ncells)
+                            const int32_t *__restrict__ receiver, const int32_t *__restrict__ slot,
+                            SegDesc *__restrict__ segs, unsigned long long *ncells)
 {
     int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end || !flag[i - begin]) return;
+    if (i >= end) return;
+    if (slot[i - begin] == (i > begin ? slot[i - begin - 1] : 0)) return;      // inclusive scan of the head flags: no step, no head
     int32_t c = order[i];
     SegDesc d;
     d.head = c; d.hmask = inmask[c];
@@ -1740,18 +1741,18 @@ static int plan_build_segments(wfa_plan *p)
     const std::vector<int32_t> &off = p->h_level_off;
     const int begin = off[1], end = off[L], n = end - begin;
     if (n <= 0) return GR2M_OK;
-    DevBuf flag, slot, temp, segoff, cnt;
-    auto cleanup = [&]() { FreeBatch fb; for (DevBuf *b : {&flag, &slot, &temp, &segoff, &cnt}) b->release(); };
+    DevBuf slot, temp, segoff, cnt;
+    auto cleanup = [&]() { FreeBatch fb; for (DevBuf *b : {&slot, &temp, &segoff, &cnt}) b->release(); };
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gr2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return e_ == cudaErrorMemoryAllocation ? GR2M_ERR_NOMEM : GR2M_ERR_CUDA; } } while (0)
 #define SRC(call) do { int r_ = (call); if (r_) { cleanup(); return r_; } } while (0)
-    SRC(flag.ensure((size_t)n * 4)); SRC(slot.ensure((size_t)n * 4)); SRC(segoff.ensure(((size_t)L + 2) * 4)); SRC(cnt.ensure(8));
+    SRC(slot.ensure((size_t)n * 4)); SRC(segoff.ensure(((size_t)L + 2) * 4)); SRC(cnt.ensure(8));
     gr2m_count_launch(), k_seg_flag<<<ceil_div(n, 256), 256, 0, st>>>(p->order.as<int32_t>(), begin, end, L, p->ncol, p->inmask.as<uint8_t>(),
-                                                                     p->level.as<int32_t>(), flag.as<int32_t>());
+                                                                     p->level.as<int32_t>(), slot.as<int32_t>());
     SCK(cudaGetLastError());
-    size_t tbytes = 0;
-    SCK(cub::DeviceScan::InclusiveSum(nullptr, tbytes, flag.as<int32_t>(), slot.as<int32_t>(), n, st));
+    size_t tbytes = 0;        // head flags -> their inclusive scan, in place
+    SCK(cub::DeviceScan::InclusiveSum(nullptr, tbytes, slot.as<int32_t>(), slot.as<int32_t>(), n, st));
     SRC(temp.ensure(tbytes));
-    SCK(cub::DeviceScan::InclusiveSum(temp.p, tbytes, flag.as<int32_t>(), slot.as<int32_t>(), n, st));
+    SCK(cub::DeviceScan::InclusiveSum(temp.p, tbytes, slot.as<int32_t>(), slot.as<int32_t>(), n, st));
     int32_t nseg = 0;
     SCK(cudaMemcpyAsync(&nseg, slot.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
     SCK(cudaStreamSynchronize(st));
@@ -1759,8 +1760,7 @@ static int plan_build_segments(wfa_plan *p)
     SRC(p->segs.ensure((size_t)nseg * sizeof(SegDesc)));
     SCK(cudaMemsetAsync(cnt.p, 0, 8, st));
     gr2m_count_launch(), k_seg_build<<<ceil_div(n, 256), 256, 0, st>>>(p->order.as<int32_t>(), begin, end, L, p->ncol, p->inmask.as<uint8_t>(),
-                                                                      p->level.as<int32_t>(), p->receiver.as<int32_t>(), flag.as<int32_t>(),
-                                                                      slot.as<int32_t>(), p->segs.as<SegDesc>(),
+                                                                      p->level.as<int32_t>(), p->receiver.as<int32_t>(), slot.as<int32_t>(), p->segs.as<SegDesc>(),
                                                                       cnt.as<unsigned long long>());
     SCK(cudaGetLastError());
     gr2m_count_launch(), k_seg_offsets<<<ceil_div(L + 1, 256), 256, 0, st>>>(p->level_off.as<int32_t>(), begin, L, slot.as<int32_t>(),
