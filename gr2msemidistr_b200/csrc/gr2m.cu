@@ -219,11 +219,11 @@ extern "C" int gr2m_release_cached_memory(void)
 // buffer with one host thread (~4-10 GB/s); here the staging is explicit: a ring of pinned buffers, the device
 // copy of one chunk overlapping the host memcpy of the others on helper threads.
 namespace {
-constexpr size_t STG_CHUNK = 16u << 20;
-constexpr int STG_NBUF = 4;
+constexpr size_t STG_CHUNK = 4u << 20;
+constexpr int STG_NBUF = 16;
 constexpr size_t STG_MIN_BYTES = 32u << 20;     // below this a plain copy is as good
 std::mutex g_stg_mu;
-void *g_stg_buf[STG_NBUF] = {nullptr, nullptr, nullptr, nullptr};
+void *g_stg_buf[STG_NBUF] = {};
 cudaEvent_t g_stg_ev[STG_NBUF];
 bool stg_init_locked()
 {
@@ -298,7 +298,7 @@ int gr2m_copy_h2d(void *dst_dev, const void *src, size_t bytes, cudaStream_t st)
     }
     const size_t nch = (bytes + STG_CHUNK - 1) / STG_CHUNK;
     std::future<void> fut[STG_NBUF];
-    bool used[STG_NBUF] = {false, false, false, false};
+    bool used[STG_NBUF] = {};
     auto fill = [&](size_t i) {     // helper thread: wait until the previous device copy out of the buffer is done, then fill it
         const int bi = (int)(i % STG_NBUF);
         const size_t o = i * STG_CHUNK, n = bytes - o < STG_CHUNK ? bytes - o : STG_CHUNK;
