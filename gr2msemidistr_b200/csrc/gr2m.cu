@@ -1010,9 +1010,10 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         // canonical groups of tiles (a function of the number of cells only): one partial sum per group, set and month,
         // so a set's outlet sums do not depend on the batch it is evaluated in nor on how many ranks share the sets
         group_tiles = 4;                 // a multiple of the cells per thread of every k_gr2m_calib4 variant
-        while (group_tiles * 2 * 32 <= b->ntiles) group_tiles *= 2;
+        while (group_tiles * 128 < b->ntiles) group_tiles *= 2;      // at most 128 groups
         const int ngroups = ceil_div(b->ntiles, group_tiles);
         int gps = (int)((long long)ngroups * nsg / ((long long)b->sm_count * 3 * 16));   // >= ~16 waves of blocks when possible
+        if (const char *ev = getenv("GR2M_CALIB_GPS")) gps = atoi(ev);      // experiment switch: canonical groups per block
         if (gps < 1) gps = 1;
         tiles_per_split = gps * group_tiles;
         csplit = ngroups;
@@ -1020,7 +1021,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         // general kernel (several regions, literal arithmetic): one block per set group and canonical group of tiles, the
         // same grouping rule, so these sums do not depend on the batch size either
         group_tiles = 4;
-        while (group_tiles * 2 * 32 <= b->ntiles) group_tiles *= 2;
+        while (group_tiles * 128 < b->ntiles) group_tiles *= 2;      // at most 128 groups
         tiles_per_split = group_tiles;
         csplit = ceil_div(b->ntiles, tiles_per_split);
     }

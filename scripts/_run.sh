@@ -1,15 +1,16 @@
 python - <<'PY'
-import time, numpy as np
+import numpy as np
 from gr2msemidistr_b200 import capi, synth
 capi.set_device(0)
-P,E,area,nd=synth.forcing(100000,480)
-reg=np.zeros(100000,np.int32)
-par=np.array(synth.SET0)
-for rep in range(4):
-    t0=time.perf_counter()
+for ncell, nsets in ((64, 8), (128, 8), (256, 8), (1024, 8), (64, 8*148*3)):
+    P,E,area,nd=synth.forcing(ncell,480)
+    reg=np.zeros(ncell,np.int32)
+    par=synth.param_sets(nsets)
+    q=synth.qobs_from(np.full(480,100.0))
     with capi.Basin(P,E,area,nd,reg,1) as b:
-        t1=time.perf_counter()
-        out=b.run(par)
-        t2=time.perf_counter()
-    print('create %.3f s  run %.3f s  run e2e %.3g cell-months/s'%(t1-t0,t2-t1,4.8e7/(t2-t1)))
+        ms=[]
+        for rep in range(5):
+            b.objective_batch(par,q,36,capi.OF_KGE,0,want_crit=False)
+            ms.append(b.last_kernel_ms())
+    print('ncell',ncell,'nsets',nsets,'kernel ms',[round(m,3) for m in ms])
 PY
