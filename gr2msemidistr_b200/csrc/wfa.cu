@@ -362,7 +362,18 @@ __global__ void __launch_bounds__(256, 8) k_accum_segments(const SegDesc *__rest
         // the head like any cell of a level sweep (its upstream rows were written by earlier launches) ...
         T acc = low[0];
         {
+            // up to three upstream rows requested together (a confluence has two or three), added in k order
             unsigned mm = st[0];
+            const unsigned m0 = mm; mm &= mm - 1;
+            const unsigned m1 = mm; mm &= mm - 1;
+            const unsigned m2 = mm; mm &= mm - 1;
+            T a0 = T(0), a1 = T(0), a2 = T(0);
+            if (m0) a0 = __ldcg(up_row(A, cell[0], __ffs(m0), ncol, ld) + j);
+            if (m1) a1 = __ldcg(up_row(A, cell[0], __ffs(m1), ncol, ld) + j);
+            if (m2) a2 = __ldcg(up_row(A, cell[0], __ffs(m2), ncol, ld) + j);
+            if (m0) acc += a0;
+            if (m1) acc += a1;
+            if (m2) acc += a2;
             while (mm) {
                 acc += __ldcg(up_row(A, cell[0], __ffs(mm), ncol, ld) + j);
                 mm &= mm - 1;
