@@ -244,7 +244,8 @@ struct SegDesc {
     uint8_t len, hmask;
     uint16_t step[SEG_K - 1];      // per absorbed cell: (flow direction of the previous cell - 1) | in-flow mask << 3
 };
-static_assert(sizeof(SegDesc) == 4 + 2 * SEG_K && (SEG_K % 2) == 0, "SegDesc is 1 + SEG_K / 2 words of 32 bits");
+static_assert(sizeof(SegDesc) % 4 == 0 && sizeof(SegDesc) >= 4 + 2 * SEG_K, "SegDesc is read as 32-bit words");
+constexpr int SEG_NW = (int)(sizeof(SegDesc) / 4);
 
 // absorbable: level in [2, seg_levels), exactly one upstream cell above level 0, and not at a segment boundary
 __device__ __forceinline__ bool seg_absorbed(int32_t c, int lev, int seg_levels, int ncol, const uint8_t *__restrict__ inmask,
@@ -322,9 +323,9 @@ __global__ void __launch_bounds__(256, 8) k_accum_segments(const SegDesc *__rest
     int len = 0;
     if (live) {
         const int32_t *w = reinterpret_cast<const int32_t *>(segs + si);
-        unsigned wd[1 + SEG_K / 2];                        // head | len, hmask, step[0] | step[1], step[2] | ...
+        unsigned wd[SEG_NW];                               // head | len, hmask, step[0] | step[1], step[2] | ...
 #pragma unroll
-        for (int q = 0; q < 1 + SEG_K / 2; ++q) wd[q] = (unsigned)__ldg(w + q);
+        for (int q = 0; q < SEG_NW; ++q) wd[q] = (unsigned)__ldg(w + q);
         cell[0] = (int32_t)wd[0];
         len = wd[1] & 0xff;
         st[0] = (wd[1] >> 8) & 0xff;
