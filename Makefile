@@ -6,7 +6,7 @@ LIB := gr2msemidistr_b200/libgr2m_b200.so
 
 lib: $(LIB)
 
-$(LIB): $(CSRC)/gr2m.cu $(CSRC)/wfa.cu $(CSRC)/d8prep.cu $(CSRC)/router.cu $(CSRC)/wfa_plan.cuh $(CSRC)/common.cuh $(CSRC)/gr2m_math.cuh $(CSRC)/exp2_tab256.inc $(CSRC)/exp2_tab2048.inc include/gr2m_b200.h
+$(LIB): $(CSRC)/gr2m.cu $(CSRC)/wfa.cu $(CSRC)/d8prep.cu $(CSRC)/router.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) include/gr2m_b200.h
 	$(NVCC) $(NVCCFLAGS) -o $@ $(CSRC)/gr2m.cu $(CSRC)/wfa.cu $(CSRC)/d8prep.cu $(CSRC)/router.cu
 
 oracle:
