@@ -450,7 +450,10 @@ struct CalibArgs {
 //    to leave a stage re-arms its mbarrier and issues the bulk copy that refills it, so fast warps
 //    run up to 3 stages ahead of slow ones instead of meeting them every stage.
 constexpr int TM2 = 8;
-constexpr int NST2 = 4;
+#ifndef GR2M_NST2
+#define GR2M_NST2 4
+#endif
+constexpr int NST2 = GR2M_NST2;
 constexpr int STAGE2_DBL = TM2 * 64;
 
 // 2^(j/2048) table in shared memory (16 KiB) -> 67 KiB per CTA, 3 CTAs (24 warps) per SM; the kernel is bound
@@ -744,8 +747,11 @@ __global__ void __launch_bounds__(128) k_objective(ObjArgs a)
 __global__ void k_debug_math(int op, int n, const double *x, const double *y, double *out)
 {
     __shared__ double tab[32], tab256[256];
+    __shared__ __align__(16) unsigned char rcb_raw[2 * 4096];       // the seed table wants a 4 KiB-aligned shared address
+    float2 *rcb = reinterpret_cast<float2 *>(rcb_raw + ((0u - smem_u32(rcb_raw)) & 4095u));
     if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     tab256[threadIdx.x & 255] = c_exp2_tab256[threadIdx.x & 255];
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) rcb[j] = g_rcbrt_lin[j];
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -764,6 +770,7 @@ __global__ void k_debug_math(int op, int n, const double *x, const double *y, do
         case 11: r = 2.0 * exp_idx2048_half(clamp_u26(x[i] * 0x1.71547652b82fep+11), g_exp2_tab2048); break;
         case 12: r = rcbrt_fast_poly(x[i]); break;
         case 13: r = div_fast3q(x[i], y[i]); break;
+        case 14: r = rcbrt_fast_tab(x[i], smem_u32(rcb)); break;
         default: r = r_round_dig(x[i], (int)y[i]); break;
     }
     out[i] = r;
@@ -1042,15 +1049,18 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     if (tabmode) {
         static const int ctas = getenv("GR2M_CALIB_CTAS") ? atoi(getenv("GR2M_CALIB_CTAS")) : 3;   // experiment switches
         static const int cpt = getenv("GR2M_CALIB_CPT") ? atoi(getenv("GR2M_CALIB_CPT")) : 2;
-        static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 0;
+        static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 3;
         const int c = cpt == 1 ? 1 : cpt == 4 ? 4 : 2;
-        const size_t smem = (size_t)(NST2 * c * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * c * SPB * 32) * sizeof(double) + NST2 * 12;
-        void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, false>;
-        if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, false>;
-        else if (c == 1) kern = ctas == 4 ? k_gr2m_calib4<false, 4, 1, false> : k_gr2m_calib4<false, 3, 1, false>;
-        else if (c == 4) kern = k_gr2m_calib4<false, 2, 4, false>;
-        else if (ctas == 2) kern = magic ? k_gr2m_calib4<false, 2, 2, true> : k_gr2m_calib4<false, 2, 2, false>;
-        else if (magic) kern = k_gr2m_calib4<false, 3, 2, true>;
+        const size_t smem = (size_t)(RCB_DBL + CALIB4_NST * c * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * c * SPB * 32) * sizeof(double) +
+                            CALIB4_NST * 12 + CALIB4_ALIGN_PAD;
+        void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, 2>;
+        if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, 2>;
+        else if (c == 1) kern = ctas == 4 ? k_gr2m_calib4<false, 4, 1, 2> : k_gr2m_calib4<false, 3, 1, 2>;
+        else if (c == 4) kern = k_gr2m_calib4<false, 2, 4, 2>;
+        else if (ctas == 2) kern = magic == 2 ? k_gr2m_calib4<false, 2, 2, 2> : k_gr2m_calib4<false, 2, 2, 0>;
+        else if (magic == 3) kern = k_gr2m_calib4<false, 3, 2, 3>;
+        else if (magic == 1) kern = k_gr2m_calib4<false, 3, 2, 1>;
+        else if (magic == 0) kern = k_gr2m_calib4<false, 3, 2, 0>;
         const int nblk_split = ceil_div(b->ntiles, tiles_per_split);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, b->stream));

@@ -18,6 +18,9 @@
 #endif
 constexpr int PT_N = 256;                 // entries per table level
 constexpr int PT_WARP_DBL = 2 * PT_N;     // doubles per warp
+constexpr unsigned CALIB4_ALIGN_PAD = 4096;   // k_gr2m_calib4 aligns its tables to 4 KiB (entry offsets are ORed into the base)
+constexpr int CALIB4_NST = 2;                 // forcing stages in flight (2, 3 and 4 measured alike; 2 leaves room for the tables)
+constexpr int RCB_DBL = 512;                  // cube-root seed table: 512 float2 = 4 KiB
 
 // per cell: frange[2c] = max_t P, frange[2c+1] = max_t E; +inf when any value is negative or not finite
 __global__ void k_cell_range(const double *__restrict__ F, int ncell, int ntime, int ntime_pad, double *__restrict__ frange)
@@ -41,32 +44,33 @@ __global__ void k_cell_range(const double *__restrict__ F, int ncell, int ntime,
 // Table-mode month step: same algebra as step_fast4 (gr2m_math.cuh), exponentials from the warp's tables.
 // t1 / t2: shared-memory byte addresses of the warp's T1h / T2; nclamp: smallest n with n c >= 26.
 // exp(n c)/2 from the warp's tables: T1h[n >> 8] * T2[n & 255]; addresses by one shift / mask and one multiply-add each
-__device__ __forceinline__ double pow_tab_half(int n, uint32_t t1, uint32_t t2)
+__device__ __forceinline__ void pow_tab_hl(int n, uint32_t t1, uint32_t t2, double &h, double &l)
 {
     uint32_t a1, a2;
     asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a1) : "r"((uint32_t)n >> 8), "r"(t1));
     asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a2) : "r"((uint32_t)n & (PT_N - 1)), "r"(t2));
-    double h, l;
     asm("ld.shared.f64 %0, [%1];" : "=d"(h) : "r"(a1));
     asm("ld.shared.f64 %0, [%1];" : "=d"(l) : "r"(a2));
-    return __dmul_rn(h, l);
 }
 
 // The part of a month that does not depend on the rounding decision's branch: stores, percolation, routing.
+// am = a2 - 1/2, ap = a2 + 1/2 (a2 = e^{2P/X1}/2), Y = 1/2 - b2 (b2 = e^{2E/X1}/2), each one FMA on the table product.
+// Evaporation: s2 = s1 / (2 b2 + s1 (1/2 - b2)) with 2 b2 = 1 - 2 Y, so the denominator is fma(s1, Y, fma(-2, Y, 1)):
+// three FMAs from the table entries (was a product, two additions and an FMA), one of them after s1; both terms are
+// positive, nothing cancels.  ctab: shared address of the cube-root seed table (rcbrt_fast_tab).
 template <bool F32EXP>
-__device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, double a2, double b2, double &s, double &rho)
+__device__ __forceinline__ double step_tab_core2(const CellPar &p, double np_, double am, double ap, double Y, double &s, double &rho,
+                                                 uint32_t ctab)
 {
-    double am = a2 - 0.5, ap = a2 + 0.5;
     double s1 = div_fast3q(__fma_rn(s, ap, am), __fma_rn(s, am, ap));
-    // (b2 + 1/2) + (1 - s1)(b2 - 1/2) = 2 b2 + s1 (1/2 - b2): one FP64 instruction less, and only one of them after s1
-    double s2 = div_fast3q(s1, __fma_rn(s1, 0.5 - b2, b2 + b2));
+    double s2 = div_fast3q(s1, __fma_rn(s1, Y, __fma_rn(-2.0, Y, 1.0)));
     double c = __fma_rn(s2 * s2, s2, 1.0);
 #if GR2M_WHATIF == 1
     double y = __fma_rn(c, -0.2, 1.0);            // no cube root: -5 FP64, -4 XU, -1 FMUL
 #elif GR2M_WHATIF == 7
-    double y = rcbrt_fast(c);                    // XU-pipe seed (F2F, LG2, EX2, F2F)
+    double y = rcbrt_fast_poly(c);               // degree-6 FP32 polynomial seed (round 2)
 #else
-    double y = rcbrt_fast_poly(c);               // c = 1 + s2^3 in [1, 2]
+    double y = rcbrt_fast_tab(c, ctab);          // c = 1 + s2^3 in [1, 2]
 #endif
     if (F32EXP) y = __fma_rn(KC.nf32_delta * (double)__logf(__double2float_rn(c)), y, y);
     double sn = s2 * y;
@@ -82,12 +86,54 @@ __device__ __forceinline__ double step_tab_core(const CellPar &p, double np_, do
     return q;
 }
 
-// Table-mode month, branch-free: the rounding decision is rint(10 f x); `tie` collects the lanes that were within
+// Table lookups of the fixed-point variant: `hi` is the high word of t = x + FX_C (below), whose bits 0..15 hold
+// n = floor(x + 1/2 + w); the tables sit at 2 KiB-aligned shared addresses, so an entry's address is two logic
+// instructions (shift, and-or) per level and n never has to exist as an integer of its own.
+__device__ __forceinline__ void pow_tab_ld(uint32_t hi, uint32_t t1, uint32_t t2, double &h, double &l)
+{
+    const uint32_t a1 = ((hi >> 5) & 0x7f8u) | t1, a2 = ((hi << 3) & 0x7f8u) | t2;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(h) : "r"(a1));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(l) : "r"(a2));
+}
+
+// 1.5 * 2^20 + 1/2 + 2^-26: for 0 <= x < 65535, t = x + FX_C lies in [2^20, 2^21), where one ulp is 2^-32: the low
+// word of t is the fraction of x + 1/2 + 2^-26 in units of 2^-32 and the low 16 bits of the high word are its integer
+// part.  A low word below 2^7 (= 2 * 2^-26) means x is within 2^-26 = 1.5e-8 of a decimal tie (the DADD's own rounding,
+// 2^-33, cannot hide one: a sum rounded up to the next integer has a zero low word); everywhere else
+// floor(x + 1/2 + 2^-26) = rint(x) = the integer R's round(f x, 1) settles on (ulp(x) <= 1.5e-11 here).
+#define GR2M_FX_C 1572864.500000014901161193847656250
+#define GR2M_FX_TIE 128u
+
+// Table-mode month, branch-free, rounding decision in fixed point (shipped): per forcing value one
+// FP64-pipe instruction, fma(10 f, x, FX_C) (was DMUL, DADD, DSETP + FRND and F2I on the conversion unit), the clamp
+// min(n, nclamp) as an integer min on the high word, the tie test as a running unsigned min of the low words (`tmin`,
+// compared with GR2M_FX_TIE once per chunk by the caller); rint(10 f P) as a double, which the routing store needs, is
+// one integer-to-double conversion of the high word's low 16 bits.
+// CLAMP = false: the caller knows that no month of the tile pair reaches nclamp (k_cell_range's maxima), the two integer
+// mins are left out.
+template <bool F32EXP, bool CLAMP>
+__device__ __forceinline__ double step_tab_fx(const CellPar &p, double Praw, double Eraw, double &s, double &rho,
+                                              uint32_t t1, uint32_t t2, uint32_t ctab, uint32_t hiclamp, uint32_t &tmin)
+{
+    // t = 10 f x + FX_C in ONE rounding (to 2^-32): integer part and tie distance of the exact product
+    const double tp = __fma_rn(p.fp10, Praw, GR2M_FX_C), te = __fma_rn(p.fe10, Eraw, GR2M_FX_C);
+    const uint32_t hp = (uint32_t)__double2hiint(tp), he = (uint32_t)__double2hiint(te);
+    const double np_ = __int2double_rn((int)(hp & 0xffffu));        // rint(10 f P) for the routing store (I2F)
+    tmin = min(tmin, min((uint32_t)__double2loint(tp), (uint32_t)__double2loint(te)));
+    double h, l;
+    pow_tab_ld(CLAMP ? min(hp, hiclamp) : hp, t1, t2, h, l);
+    const double am = __fma_rn(h, l, -0.5), ap = __fma_rn(h, l, 0.5);
+    pow_tab_ld(CLAMP ? min(he, hiclamp) : he, t1, t2, h, l);
+    return step_tab_core2<F32EXP>(p, np_, am, ap, __fma_rn(-h, l, 0.5), s, rho, ctab);
+}
+
+// Table-mode month, branch-free (round-2 form, kept as an experiment switch GR2M_CALIB_MAGIC=0|1): the rounding
+// decision is rint(10 f x); `tie` collects the lanes that were within
 // 1e-8 of a decimal tie (|10 f x| < 2^16 here, ulp <= 1.5e-11: R's candidate comparison cannot disagree with rint
 // outside that window).  The caller repeats the 8-month chunk with step_tab when any lane raised it.
-template <bool F32EXP, bool MAGIC>
+template <bool F32EXP, int MAGIC>
 __device__ __forceinline__ double step_tab_nb(const CellPar &p, double Praw, double Eraw, double &s, double &rho,
-                                              uint32_t t1, uint32_t t2, int nclamp, bool &tie)
+                                              uint32_t t1, uint32_t t2, uint32_t ctab, int nclamp, bool &tie)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
     double np_, ne_;
@@ -97,38 +143,22 @@ __device__ __forceinline__ double step_tab_nb(const CellPar &p, double Praw, dou
         ip = __double2loint(tp); ie = __double2loint(te);
         np_ = __dadd_rn(tp, KC.nmagic); ne_ = __dadd_rn(te, KC.nmagic);
     } else {
-#if GR2M_WHATIF == 3
-        np_ = xp10; ne_ = xe10; ip = __double2loint(xp10) & 0xffff; ie = __double2loint(xe10) & 0xffff;   // no conversions: -4 XU
-#else
         np_ = rint(xp10); ne_ = rint(xe10);
         ip = __double2int_rn(xp10); ie = __double2int_rn(xe10);
-#endif
     }
-#if GR2M_WHATIF == 8
-    // decided on the high words by the integer ALU instead of two DSETP (0x3FDFFFFF00000000 = 0.49999994; a NaN compares
-    // above it): 0.6 % faster on the 1.2e10-unit slice, 4 % SLOWER on the 4.8e11-unit launch -- measured, not shipped
-    const unsigned hp = (unsigned)__double2hiint(__dsub_rn(xp10, np_)) & 0x7fffffffu;
-    const unsigned he = (unsigned)__double2hiint(__dsub_rn(xe10, ne_)) & 0x7fffffffu;
-    tie |= max(hp, he) >= 0x3FDFFFFFu;
-#else
     const bool okp = fabs(__dsub_rn(xp10, np_)) < KC.tie_thr_tab, oke = fabs(__dsub_rn(xe10, ne_)) < KC.tie_thr_tab;
     tie |= !(okp & oke);
-#endif
-#if GR2M_WHATIF == 2
-    const double a2 = __fma_rn(xp10, 1e-4, 0.6), b2 = __fma_rn(xe10, 1e-4, 0.6);   // no table lookups: -4 LDS, -10 integer
-#elif GR2M_WHATIF == 4
-    const double a2 = pow_tab_half(1234, t1, t2) + xp10, b2 = pow_tab_half(77, t1, t2) + xe10;   // uniform lookups (no bank conflicts)
-#else
-    const double a2 = pow_tab_half(min(ip, nclamp), t1, t2);
-    const double b2 = pow_tab_half(min(ie, nclamp), t1, t2);
-#endif
-    return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
+    double h, l, am, ap;
+    pow_tab_hl(min(ip, nclamp), t1, t2, h, l);
+    am = __fma_rn(h, l, -0.5); ap = __fma_rn(h, l, 0.5);
+    pow_tab_hl(min(ie, nclamp), t1, t2, h, l);
+    return step_tab_core2<F32EXP>(p, np_, am, ap, __fma_rn(-h, l, 0.5), s, rho, ctab);
 }
 
 // Same month with the exact rounding path taken by the lanes that need it (R's candidate comparison).
 template <bool F32EXP>
 __device__ __forceinline__ double step_tab(const CellPar &p, const double *__restrict__ par, double Praw, double Eraw,
-                                           double &s, double &rho, uint32_t t1, uint32_t t2, int nclamp)
+                                           double &s, double &rho, uint32_t t1, uint32_t t2, uint32_t ctab, int nclamp)
 {
     double xp10 = __dmul_rn(p.fp10, Praw), xe10 = __dmul_rn(p.fe10, Eraw);
     double np_ = rint(xp10), ne_ = rint(xe10);
@@ -140,142 +170,12 @@ __device__ __forceinline__ double step_tab(const CellPar &p, const double *__res
         ip = __double2int_rn(np_);
         ie = __double2int_rn(ne_);
     }
-    const double a2 = pow_tab_half(min(ip, nclamp), t1, t2);
-    const double b2 = pow_tab_half(min(ie, nclamp), t1, t2);
-    return step_tab_core<F32EXP>(p, np_, a2, b2, s, rho);
+    double h, l, am, ap;                   // the same fused half terms as the branch-free pass: same bits either way
+    pow_tab_hl(min(ip, nclamp), t1, t2, h, l);
+    am = __fma_rn(h, l, -0.5); ap = __fma_rn(h, l, 0.5);
+    pow_tab_hl(min(ie, nclamp), t1, t2, h, l);
+    return step_tab_core2<F32EXP>(p, np_, am, ap, __fma_rn(-h, l, 0.5), s, rho, ctab);
 }
-
-template <bool F32EXP, int CTAS, int NST, bool MAGIC>
-__global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);            // NST * STAGE2_DBL
-    double *ptab = stage + NST * STAGE2_DBL;                        // SPB * PT_WARP_DBL
-    double *saved = ptab + SPB * PT_WARP_DBL;                        // 2 * SPB * 32: stores at the start of a chunk
-    uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * SPB * 32);   // NST
-    int *left = reinterpret_cast<int *>(full + NST);                // NST: warps that have left the stage
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
-    const int set = sg * SPB + warp;
-    const bool set_ok = set < a.nsets;
-    const int tile0 = cs * a.tiles_per_split;
-    const int tile1 = min(a.ntiles, tile0 + a.tiles_per_split);
-    const int nchunk = a.ntime_pad / TM2;
-    const int total = (tile1 - tile0) * nchunk;
-
-    if (tid < NST) left[tid] = 0;
-    if (tid == 0) {
-        for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const double *Fbase = a.F + (size_t)tile0 * a.ntime_pad * 64;
-    if (tid == 0) {
-        for (int g = 0; g < NST && g < total; ++g) {
-            mbar_arrive_expect_tx(&full[g], STAGE2_DBL * 8);
-            bulk_g2s(stage + g * STAGE2_DBL, Fbase + (size_t)g * STAGE2_DBL, STAGE2_DBL * 8, &full[g]);
-        }
-    }
-
-    // one region: every lane of the warp has the set's parameters (only the area differs)
-    const double *par = a.params + (size_t)(set_ok ? set : 0) * 4;
-    CellPar p = load_par(par, 1, 0, 0.0, a.forcing_ok);
-    // smallest n whose argument n c reaches the clamp 26 (airGR: min(P/X1, 13)); tables hold exp(min(., 26))
-    const double U26 = 0x1.2c14a02335a6fp+16;                       // 26 * 2048 / ln 2
-    const double ncd = ceil(U26 / p.g);
-    const int nclamp = ncd < 1073741824.0 ? (int)ncd : 1073741824;   // NaN parameters: results are NaN anyway
-    double *mytab = ptab + warp * PT_WARP_DBL;
-    for (int i = lane; i < PT_N; i += 32) {
-        mytab[i] = exp_idx2048_half(clamp_u26((double)(i * PT_N) * p.g), g_exp2_tab2048);            // T1h
-        mytab[PT_N + i] = 2.0 * exp_idx2048_half(clamp_u26((double)i * p.g), g_exp2_tab2048);        // T2
-    }
-    __syncwarp();
-    const uint32_t t1 = smem_u32(mytab), t2 = t1 + PT_N * 8;
-    const bool set_tab = p.thr >= 0.0 && p.X1 >= 1.0 && p.fp10 >= 0.0 && p.fe10 >= 0.0;
-
-    double *myout = a.partial + ((size_t)cs * a.nsets + (set_ok ? set : 0)) * a.ntime;
-    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    const bool writer = set_ok && (lane & 3) == 0;
-    int g = 0, nredo = 0;
-    const int g0 = 0;
-    bool branchy = false;
-    for (int tile = tile0; tile < tile1; ++tile) {
-        const int cell = tile * 32 + lane;
-        const bool cell_ok = cell < a.ncell;
-        p.area = cell_ok ? a.area[cell] : 0.0;
-        // table mode needs 0 <= 10 f x < 65535 for every month of every lane (+inf marks negative / non-finite forcing)
-        bool lane_tab = set_tab;
-        if (cell_ok) lane_tab = lane_tab && (p.fp10 * a.frange[2 * cell] < 65535.0) && (p.fe10 * a.frange[2 * cell + 1] < 65535.0);
-        const bool use_tab = __all_sync(0xffffffffu, lane_tab);
-        double S = 0.3, R = 0.5 * p.X2 * p.iX1;                    // stores divided by X1; airGR starts at 0.3 X1, 0.5 X2
-        const double aX1 = p.area * p.X1;
-        for (int ch = 0; ch < nchunk; ++ch, ++g) {
-            const int st = g % NST;
-            mbar_wait(&full[st], (g / NST) & 1);
-            if (set_ok) {
-                const double *sp = stage + st * STAGE2_DBL + lane;
-                bool redo = true;
-                if (use_tab && !branchy) {
-                    // branch-free pass over the 8 months; repeated below if a lane sat on a rounding tie
-                    saved[tid] = S;
-                    saved[SPB * 32 + tid] = R;
-                    bool tie = false;
-                    double v[8];
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) v[m] = aX1 * step_tab_nb<F32EXP, MAGIC>(p, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp, tie);
-                    redo = __any_sync(0xffffffffu, tie);
-#if GR2M_WHATIF != 0 && GR2M_WHATIF != 8
-                    redo = false;
-#endif
-                    if (!redo) {
-#if GR2M_WHATIF == 6
-                        double s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));   // no cross-lane reduction
-#else
-                        double s = warp_reduce8(v, lane);
-#endif
-                        const int t = ch * TM2 + ridx;
-                        if (writer && t < a.ntime) atomicAdd(myout + t, s * __ldg(a.tconv + t));
-                    } else {
-                        S = saved[tid];
-                        R = saved[SPB * 32 + tid];
-                        // parameter sets whose factors make ties common (e.g. three-decimal factors on one-decimal
-                        // forcing: one value in a thousand) go month by month for the rest of the launch
-                        nredo += 16;
-                        branchy = nredo > g - g0 + 64;
-                    }
-                }
-                if (redo) {
-                    // month by month (ties, or the general formulation); the butterfly adds in warp_reduce8's order
-#pragma unroll 1
-                    for (int m = 0; m < 8; ++m) {
-                        double q = use_tab ? step_tab<F32EXP>(p, par, sp[m * 64], sp[m * 64 + 32], S, R, t1, t2, nclamp)
-                                           : step_fast4<F32EXP>(p, sp[m * 64], sp[m * 64 + 32], S, R, g_exp2_tab2048);
-                        q = warp_sum_f64(aX1 * q);
-                        const int t = ch * TM2 + m;
-                        if (lane == 0 && t < a.ntime) atomicAdd(myout + t, q * __ldg(a.tconv + t));
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                // this warp's reads of the stage are complete; release / acquire on left[st] orders them before the refill
-                __threadfence_block();
-                if (atomicAdd(&left[st], 1) == SPB - 1) {
-                    __threadfence_block();
-                    left[st] = 0;
-                    const int gn = g + NST;
-                    if (gn < total) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive_expect_tx(&full[st], STAGE2_DBL * 8);
-                        bulk_g2s(stage + st * STAGE2_DBL, Fbase + (size_t)gn * STAGE2_DBL, STAGE2_DBL * 8, &full[st]);
-                    }
-                }
-            }
-        }
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------------------
 // k_gr2m_calib4: the same table-mode recursion with CPT cells per thread and canonical partial sums.
@@ -287,14 +187,19 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib3(CalibArgs a)
 //    the number of ranks or the SM count (k_objective adds the groups in index order).
 // ---------------------------------------------------------------------------------------------------------
 
-template <bool F32EXP, int CTAS, int CPT, bool MAGIC>
+//  * MAGIC = 2 (shipped): rounding decision in fixed point (step_tab_fx); 0 / 1: the round-2 forms (step_tab_nb).
+template <bool F32EXP, int CTAS, int CPT, int MAGIC>
 __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
 {
-    constexpr int NST = NST2, STG = CPT * STAGE2_DBL;
+    constexpr int NST = CALIB4_NST, STG = CPT * STAGE2_DBL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);            // NST * STG
-    double *ptab = stage + NST * STG;                                // SPB * PT_WARP_DBL
-    double *saved = ptab + SPB * PT_WARP_DBL;                        // 2 * CPT * SPB * 32: stores at the start of a chunk
+    // the tables come first, at a 4 KiB-aligned shared address (pow_tab_ld / rcbrt_fast_tab OR the entry offset into
+    // the base); the launch asks for CALIB4_ALIGN_PAD more bytes than the layout needs
+    unsigned char *smem_al = smem_raw + ((0u - smem_u32(smem_raw)) & (CALIB4_ALIGN_PAD - 1));
+    double *rcb = reinterpret_cast<double *>(smem_al);               // RCB_DBL: cube-root seed table (float2 entries)
+    double *ptab = rcb + RCB_DBL;                                    // SPB * PT_WARP_DBL
+    double *stage = ptab + SPB * PT_WARP_DBL;                        // NST * STG
+    double *saved = stage + NST * STG;                               // 2 * CPT * SPB * 32: stores at the start of a chunk
     uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * CPT * SPB * 32);   // NST
     int *left = reinterpret_cast<int *>(full + NST);                 // NST: warps that have left the stage
 
@@ -313,6 +218,8 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
         for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
         mbar_fence_init();
     }
+    for (int i = tid; i < RCB_DBL; i += SPB * 32) reinterpret_cast<float2 *>(rcb)[i] = g_rcbrt_lin[i];
+    const uint32_t ctab = smem_u32(rcb);
     __syncthreads();
     // stage gi = 8 months (chunk gi % nchunk) of the CPT tiles of pair gi / nchunk: one 4 KiB bulk copy per tile
     auto issue = [&](int gi) {
@@ -341,6 +248,9 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
     __syncwarp();
     const uint32_t t1 = smem_u32(mytab), t2 = t1 + PT_N * 8;
     const bool set_tab = p.thr >= 0.0 && p.X1 >= 1.0 && p.fp10 >= 0.0 && p.fe10 >= 0.0;
+    // high word of min(nclamp, 65535) + FX_C: the clamp is an unsigned min on the high word of x + FX_C
+    const uint32_t hiclamp = (uint32_t)__double2hiint((double)min(nclamp, 65535) + GR2M_FX_C);
+    const double nclamp_m1 = (double)nclamp - 1.0;                   // 10 f x below it: floor(10 f x + 1/2 + 2^-26) < nclamp
 
     const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const bool writer = set_ok && (lane & 3) == 0;
@@ -351,7 +261,7 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
         double *myout = a.partial + ((size_t)(tA / a.group_tiles) * a.nsets + (set_ok ? set : 0)) * a.ntime;
         double aX1[CPT], S[CPT], R[CPT];
         int soff[CPT];                  // a missing last tile re-reads the first one's forcing with area 0
-        bool lane_tab = set_tab;
+        bool lane_tab = set_tab, lane_noclamp = MAGIC == 3;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const bool has = tA + c < tile1;
@@ -360,11 +270,16 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
             aX1[c] = (cell_ok ? a.area[cell] : 0.0) * p.X1;
             soff[c] = (has ? c : 0) * STAGE2_DBL + lane;
             // table mode needs 0 <= 10 f x < 65535 for every month of every lane (+inf marks negative / non-finite forcing)
-            if (cell_ok) lane_tab = lane_tab && (p.fp10 * a.frange[2 * cell] < 65535.0) && (p.fe10 * a.frange[2 * cell + 1] < 65535.0);
+            if (cell_ok) {
+                const double xpm = p.fp10 * a.frange[2 * cell], xem = p.fe10 * a.frange[2 * cell + 1];
+                lane_tab = lane_tab && (xpm < 65535.0) && (xem < 65535.0);
+                lane_noclamp = lane_noclamp && (xpm < nclamp_m1) && (xem < nclamp_m1);
+            }
             S[c] = 0.3;                                               // stores divided by X1; airGR starts at 0.3 X1, 0.5 X2
             R[c] = 0.5 * p.X2 * p.iX1;
         }
         const bool use_tab = __all_sync(0xffffffffu, lane_tab);
+        const bool no_clamp = MAGIC == 3 && __all_sync(0xffffffffu, lane_noclamp);   // no month of the pair reaches nclamp
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
             const int st = g % NST;
             mbar_wait(&full[st], (g / NST) & 1);
@@ -379,14 +294,32 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
                         saved[(2 * c + 1) * SPB * 32 + tid] = R[c];
                     }
                     bool tie = false;
+                    uint32_t tmin = 0xffffffffu;
                     double v[8];
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        v[m] = aX1[0] * step_tab_nb<F32EXP, MAGIC>(p, sp[soff[0] + m * 64], sp[soff[0] + m * 64 + 32], S[0], R[0], t1, t2, nclamp, tie);
+                    if (MAGIC == 3 && no_clamp) {
 #pragma unroll
-                        for (int c = 1; c < CPT; ++c)
-                            v[m] = __fma_rn(aX1[c], step_tab_nb<F32EXP, MAGIC>(p, sp[soff[c] + m * 64], sp[soff[c] + m * 64 + 32], S[c], R[c], t1, t2, nclamp, tie), v[m]);
+                        for (int m = 0; m < 8; ++m) {
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
+                                const double qc = step_tab_fx<F32EXP, false>(p, Pr, Er, S[c], R[c], t1, t2, ctab, hiclamp, tmin);
+                                v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
+                                const double qc = MAGIC >= 2 ? step_tab_fx<F32EXP, true>(p, Pr, Er, S[c], R[c], t1, t2, ctab, hiclamp, tmin)
+                                                             : step_tab_nb<F32EXP, MAGIC>(p, Pr, Er, S[c], R[c], t1, t2, ctab, nclamp, tie);
+                                v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                            }
+                        }
                     }
+                    if (MAGIC >= 2) tie = tmin < GR2M_FX_TIE;
                     redo = __any_sync(0xffffffffu, tie);
                     if (!redo) {
                         double s = warp_reduce8(v, lane);
@@ -412,7 +345,7 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) {
                             const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
-                            const double qc = use_tab ? step_tab<F32EXP>(p, par, Pr, Er, S[c], R[c], t1, t2, nclamp)
+                            const double qc = use_tab ? step_tab<F32EXP>(p, par, Pr, Er, S[c], R[c], t1, t2, ctab, nclamp)
                                                       : step_fast4<F32EXP>(p, Pr, Er, S[c], R[c], g_exp2_tab2048);
                             q = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, q);
                         }

@@ -271,6 +271,14 @@ __device__ __forceinline__ double rcbrt_fast_poly(double c)
 {
     const float cf = __int_as_float(__funnelshift_l(__double2loint(c), __double2hiint(c), 3) + 0x40000000);
     const float t = cf - 1.5f;
+#ifdef GR2M_CBRT_DEG5       /* experiment: degree 5 (2^-17.4): Halley residual ~4 ulp per month */
+    float y0 = -0.017018644139170647f;
+    y0 = fmaf(y0, t, 0.028428999707102776f);
+    y0 = fmaf(y0, t, -0.04437178745865822f);
+    y0 = fmaf(y0, t, 0.08593161404132843f);
+    y0 = fmaf(y0, t, -0.1941416710615158f);
+    y0 = fmaf(y0, t, 0.8735854029655457f);
+#else
     float y0 = 0.01006671879440546f;
     y0 = fmaf(y0, t, -0.016902167350053787f);
     y0 = fmaf(y0, t, 0.024652300402522087f);
@@ -278,7 +286,31 @@ __device__ __forceinline__ double rcbrt_fast_poly(double c)
     y0 = fmaf(y0, t, 0.08628594130277634f);
     y0 = fmaf(y0, t, -0.19413940608501434f);
     y0 = fmaf(y0, t, 0.8735804557800293f);
+#endif
     const int yb = __float_as_int(y0);
+    const double y = __hiloint2double((int)((unsigned)yb >> 3) + 0x38000000, yb << 29);
+    double y3 = __dmul_rn(__dmul_rn(y, y), y);
+    double e = __fma_rn(-c, y3, 1.0);
+    double q = __fma_rn(e, KC.two_ninths, KC.third);
+    return __fma_rn(__dmul_rn(y, e), q, y);
+}
+
+// (a, b) of a piecewise-linear FP32 seed of c^(-1/3) on [1, 2] (256 intervals; scripts/gen_rcbrt_table.py), 4 KiB
+__device__ const float2 g_rcbrt_lin[512] = {
+#include "rcbrt_lin256.inc"
+};
+
+// Same for c in [1, 2] with the seed read from a shared-memory copy of g_rcbrt_lin at the 4 KiB-aligned shared address
+// `tab`: the entry index is bits 20..12 of the high word (lowest exponent bit + 8 mantissa bits, so c = 2.0 has its own
+// entry), seed = a + b c in one FFMA, 2^-20.8; then the same Halley step (final error <= 1 ulp).  7 ALU / LSU / FMA-pipe
+// instructions instead of the polynomial's 10.
+__device__ __forceinline__ double rcbrt_fast_tab(double c, uint32_t tab)
+{
+    const uint32_t hi = (uint32_t)__double2hiint(c);
+    const float cf = __int_as_float(__funnelshift_l(__double2loint(c), hi, 3) + 0x40000000);
+    float a, b;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(((hi >> 9) & 0xff8u) | tab));
+    const int yb = __float_as_int(fmaf(b, cf, a));
     const double y = __hiloint2double((int)((unsigned)yb >> 3) + 0x38000000, yb << 29);
     double y3 = __dmul_rn(__dmul_rn(y, y), y);
     double e = __fma_rn(-c, y3, 1.0);

@@ -65,6 +65,10 @@ def test_device_math_building_blocks(capi, oracle, rng):
     assert np.max(np.abs(capi.debug_math(4, c) * np.cbrt(c) - 1)) < 7e-16
     assert np.max(np.abs(capi.debug_math(12, c) * np.cbrt(c) - 1)) < 7e-16         # seed without the XU pipe (c in [1, 2])
     assert np.isnan(capi.debug_math(12, np.array([np.nan])))[0]
+    # shipped: piecewise-linear table seed (c in [1, 2], 2.0 included: it has its own table entry)
+    cc = np.concatenate([c[(c >= 1) & (c <= 2)], np.linspace(1.0, 2.0, 100001), 1 + np.arange(257) / 256.0,
+                         np.nextafter(1 + np.arange(1, 257) / 256.0, 0.0)])
+    assert np.max(np.abs(capi.debug_math(14, cc) * np.cbrt(cc) - 1)) < 7e-16
 
 
 @pytest.mark.parametrize("flags", [0, 16, 1, 17])
