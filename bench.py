@@ -423,7 +423,7 @@ def main():
     rate = units_kernel / (kernel_ms * 1e-3)
     ach_tf = rate * FLOP_PER_UNIT_ALGO / 1e12                       # algorithmic flops per unit x units / time
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": None, "kernel": "k_gr2m_calib4<cells per thread 2>" if not a.literal else "k_gr2m_calib2<literal>",
+                "traffic": None, "kernel": "k_gr2m_calib4<cells per thread 2, fixed-point rounding>" if not a.literal else "k_gr2m_calib2<literal>",
                 "kernel_ms": kernel_ms, "units_per_launch": units_kernel,
                 "algorithmic_flop_per_unit": FLOP_PER_UNIT_ALGO,
                 "achieved_def": "SURVEY 8(d) algorithmic count (67 FP64 operations per subbasin x set x month, every add / "
@@ -443,7 +443,12 @@ def main():
             "achieved_executed_tflops": rate * NCU["executed_flop_per_unit"] / 1e12,
             "achieved_executed_def": "2 x DFMA + DMUL + DADD thread instructions per unit from the ncu op counters x units / time",
             "fp64_pipe_inst_per_unit": NCU["fp64_pipe_inst_per_unit"], "all_inst_per_unit": NCU["all_thread_inst_per_unit"],
-            "fp64_pipe_busy_ncu": NCU["fp64_pipe_busy"], "issue_active_ncu": NCU["issue_active"]})
+            "fp64_pipe_busy_ncu": NCU["fp64_pipe_busy"], "issue_active_ncu": NCU["issue_active"],
+            "smem_pipe_busy_ncu": NCU.get("smem_pipe_busy"),
+            "smem_wavefronts_per_warp_unit": NCU.get("smem_wavefronts_per_warp_unit"),
+            "limiter_note": "two co-limiters (ncu, profiles/r2_calib4_ncu_full.txt): issue slots (an FP64-pipe instruction takes 2, "
+                            "62 % busy) and the shared-memory data pipe (25 wavefronts per warp and unit, 9 of them bank "
+                            "conflicts of the random table lookups, 75 % busy)"})
 
     # ---- end to end through the host-buffer C ABI ---------------------------------------------
     e2e = None

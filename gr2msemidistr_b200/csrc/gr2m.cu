@@ -1056,7 +1056,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, 2>;
         if (a.f32exp) kern = k_gr2m_calib4<true, 3, 2, 2>;
         else if (c == 1) kern = ctas == 4 ? k_gr2m_calib4<false, 4, 1, 2> : k_gr2m_calib4<false, 3, 1, 2>;
-        else if (c == 4) kern = k_gr2m_calib4<false, 2, 4, 2>;
+        else if (c == 4) kern = k_gr2m_calib4<false, 2, 4, 3>;
         else if (ctas == 2) kern = magic == 2 ? k_gr2m_calib4<false, 2, 2, 2> : k_gr2m_calib4<false, 2, 2, 0>;
         else if (magic == 3) kern = k_gr2m_calib4<false, 3, 2, 3>;
         else if (magic == 1) kern = k_gr2m_calib4<false, 3, 2, 1>;

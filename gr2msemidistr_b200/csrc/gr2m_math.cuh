@@ -70,7 +70,7 @@ __constant__ MathK KC = {GR2M_MAGIC,
                          0x1.62e42fefa39efp-12,       // L = ln2/2048
                          0x1.ebfbdff82c58fp-25,       // L^2/2
                          0x1.c6b08d704a0c0p-38,       // L^3/6
-                         0.49999999};                 // tie window of the table-mode kernel (|10 f x| < 2^16), gr2m_calib3.cuh
+                         0.49999999};                 // tie window of the round-2 table-mode step (|10 f x| < 2^16), gr2m_calib3.cuh
 
 // ---- R round(x, 1) ------------------------------------------------------------------------------
 // Correctly rounded n/10 for integer-valued |n| < 2^52 (Markstein: 0.1 is RN(1/10), q0 faithful).
@@ -271,14 +271,6 @@ __device__ __forceinline__ double rcbrt_fast_poly(double c)
 {
     const float cf = __int_as_float(__funnelshift_l(__double2loint(c), __double2hiint(c), 3) + 0x40000000);
     const float t = cf - 1.5f;
-#ifdef GR2M_CBRT_DEG5       /* experiment: degree 5 (2^-17.4): Halley residual ~4 ulp per month */
-    float y0 = -0.017018644139170647f;
-    y0 = fmaf(y0, t, 0.028428999707102776f);
-    y0 = fmaf(y0, t, -0.04437178745865822f);
-    y0 = fmaf(y0, t, 0.08593161404132843f);
-    y0 = fmaf(y0, t, -0.1941416710615158f);
-    y0 = fmaf(y0, t, 0.8735854029655457f);
-#else
     float y0 = 0.01006671879440546f;
     y0 = fmaf(y0, t, -0.016902167350053787f);
     y0 = fmaf(y0, t, 0.024652300402522087f);
@@ -286,7 +278,6 @@ __device__ __forceinline__ double rcbrt_fast_poly(double c)
     y0 = fmaf(y0, t, 0.08628594130277634f);
     y0 = fmaf(y0, t, -0.19413940608501434f);
     y0 = fmaf(y0, t, 0.8735804557800293f);
-#endif
     const int yb = __float_as_int(y0);
     const double y = __hiloint2double((int)((unsigned)yb >> 3) + 0x38000000, yb << 29);
     double y3 = __dmul_rn(__dmul_rn(y, y), y);
@@ -302,16 +293,15 @@ __device__ const float2 g_rcbrt_lin[512] = {
 
 // Same for c in [1, 2] with the seed read from a shared-memory copy of g_rcbrt_lin at the 4 KiB-aligned shared address
 // `tab`: the entry index is bits 20..12 of the high word (lowest exponent bit + 8 mantissa bits, so c = 2.0 has its own
-// entry), seed = a + b c in one FFMA, 2^-20.8; then the same Halley step (final error <= 1 ulp).  7 ALU / LSU / FMA-pipe
-// instructions instead of the polynomial's 10.
+// entry), seed = a + b c in one FFMA, 2^-20.8; then the same Halley step (final error <= 1 ulp).  6 instructions
+// before the Halley step instead of the polynomial's 10.
 __device__ __forceinline__ double rcbrt_fast_tab(double c, uint32_t tab)
 {
     const uint32_t hi = (uint32_t)__double2hiint(c);
     const float cf = __int_as_float(__funnelshift_l(__double2loint(c), hi, 3) + 0x40000000);
     float a, b;
     asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(((hi >> 9) & 0xff8u) | tab));
-    const int yb = __float_as_int(fmaf(b, cf, a));
-    const double y = __hiloint2double((int)((unsigned)yb >> 3) + 0x38000000, yb << 29);
+    const double y = (double)fmaf(b, cf, a);       // one F2F on the conversion unit (two integer instructions measured the same)
     double y3 = __dmul_rn(__dmul_rn(y, y), y);
     double e = __fma_rn(-c, y3, 1.0);
     double q = __fma_rn(e, KC.two_ninths, KC.third);

@@ -197,6 +197,29 @@ def test_objective_extreme_parameter_sets(capi, oracle):
         assert np.array_equal(np.isfinite(got["crit"]), ok) and relerr(got["crit"][ok], ref["crit"][ok]) <= TOL
 
 
+def test_objective_rounding_ties_in_table_mode(capi, oracle, rng):
+    # the table-mode kernel decides round(f x, 1) in fixed point (one FMA, tie window 2^-26 on 10 f x, chunk redo through
+    # R's candidate comparison): forcing placed on, just beside and far from decimal ties of f x for "nice" and random
+    # factors, zero months (10 f x = 0 exactly), values that are exact eighths of a tenth -- one region, several tile pairs
+    ncell, ntime = 150, 64
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=71)
+    k = rng.integers(0, 4000, (ncell, ntime)).astype(np.float64)
+    delta = rng.choice([0.0, 1e-13, -1e-13, 1e-10, -1e-10, 3e-9, -3e-9, 2e-8, -2e-8, 1e-6, 0.0125, 0.025], (ncell, ntime))
+    tie = rng.random((ncell, ntime)) < 0.5
+    P = np.where(tie, (k + 0.5 + delta) / 10.0, P)                     # f = 1: 10 f x = k + 1/2 + delta
+    E = np.where(rng.random((ncell, ntime)) < 0.3, (rng.integers(0, 2000, (ncell, ntime)) + 0.5) / 12.5, E)   # f = 1.25
+    P[5] = 0.0; E[6] = 0.0; P[7] = 0.05; P[8, ::3] = 6553.45
+    par = synth.param_sets(24, seed=72)
+    par[:8, 2:] = [[1.0, 1.0], [1.0, 1.25], [1.25, 1.0], [0.8, 1.2], [1.186, 1.169], [1.001, 0.999], [1.2, 0.8], [1.125, 0.875]]
+    par[8:12, 0] = [1.0, 3.0, 40.0, 2000.0]                            # with and without the min(P / X1, 13) clamp
+    region = np.zeros(ncell, np.int32)
+    qobs = synth.qobs_from(np.full(ntime, 150.0))
+    with capi.Basin(P, E, area, nd, region, 1) as b:
+        got = b.objective_batch(par, qobs, 6, capi.OF_NSE, capi.SINK_UNROUNDED, want_qt=True)
+    ref = oracle.objective_batch(P, E, area, nd, region, 1, par, qobs, 6, flags=oracle.SINK_UNROUNDED, nthreads=4)
+    assert relerr(got["qt"], ref["qt"]) <= TOL
+
+
 def test_objective_single_subbasin_branch(capi, oracle):
     # nsub == 1: sink is the unrounded QS (Optim:187-188)
     P, E, area, nd = synth.forcing(1, 120, seed=31)
