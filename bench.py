@@ -197,6 +197,29 @@ def cpu_routing(a):
                       f"one month per thread"}
 
 
+def bench_routed_calibration(a, capi, router, nsub, months, nsets=256):
+    """north_star's whole loop at a gauge: simulate every candidate set, route sets x months through the routing operator,
+    score the routed discharge of one polygon (Run -> Routing -> hydroGOF), through the host-buffer call a calibration
+    driver makes (gr2m_objective_routed_batch: parameters up, objectives down)."""
+    from gr2msemidistr_b200 import synth
+    P, E, area, nd = synth.forcing(nsub, months, seed=4321)
+    par = synth.param_sets(nsets, seed=4322)
+    qobs = synth.qobs_from(np.full(months, 5.0e4))
+    gauge = nsub - 1                   # south-east corner block: the tilt drains towards it
+    with capi.Basin(P, E, area, nd, np.zeros(nsub, np.int32), 1) as b:
+        b.objective_routed_batch(router, par[:32], qobs, gauge, warmup=36, which=capi.OF_KGE)
+        t0 = time.perf_counter()
+        got = b.objective_routed_batch(router, par, qobs, gauge, warmup=36, which=capi.OF_KGE)
+        dt = time.perf_counter() - t0
+        kern_ms = b.last_kernel_ms()
+    units = float(nsub) * months * nsets
+    return {"workload": f"{nsub} subbasins x {nsets} parameter sets x {months} months: GR2M simulation of every set, "
+                        f"sets x months routed through the operator, KGE of the routed discharge at polygon {gauge}",
+            "value": units / dt, "unit": UNIT, "seconds": dt, "device_ms": kern_ms, "sets_per_s": nsets / dt,
+            "finite_objectives": int(np.isfinite(got["of"]).sum()),
+            "api": "gr2m_objective_routed_batch (host parameters in, objectives out)"}
+
+
 def bench_router(a, capi, torch, plan, n, months, dense_ms_one_gpu):
     """Routing as Routing_GR2MSemiDistr uses it (one value per subbasin, per-polygon maximum): the
     month-invariant operator built once for the geometry, then applied to all months."""
@@ -219,9 +242,15 @@ def bench_router(a, capi, torch, plan, n, months, dense_ms_one_gpu):
         e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
     info = router.info()
+    del QS, QR
+    try:
+        routed = bench_routed_calibration(a, capi, router, nsub, months)
+    except Exception as ex:           # tertiary figure: report, do not lose the operator numbers
+        routed = {"error": repr(ex)}
     router.close()
     return {"workload": f"{nsub} subbasins ({nb} x {nb} blocks) on the same {n} x {n} grid x {months} months, QS resident",
             "build_s": t_build, "apply_ms": best, "dense_sweep_ms_same_months": dense_ms_one_gpu,
+            "routed_calibration": routed,
             "interior_cells": int(off[-1]), **info,
             "note": "same QR as the dense sweep, bit for bit (tests/test_gpu_router.py); build includes the H2D of the "
                     "polygon cell lists and is paid once per geometry"}

@@ -571,13 +571,19 @@ struct SimArgs {
 // tile [series][cell][month] and written out as runs of SIM_MB consecutive months per subbasin (128-byte segments),
 // so no transposed copy of the 5 x [ntime x ncell] outputs is ever made.
 constexpr int SIM_MB = 16, SIM_WARPS = 4, SIM_LD = SIM_MB + 1;
+constexpr int SIM_SMEM_MAX = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * (int)sizeof(double);     // all five series wanted
 
 template <bool FAST>
 __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
 {
     extern __shared__ double sim_smem[];
     double *tab = sim_smem;                                                      // 32: 2^(j/32)
-    double *tile = sim_smem + 32 + (threadIdx.x >> 5) * (5 * 32 * SIM_LD);       // [5][32][SIM_LD]
+    // only the wanted series get a tile (the routed objective wants QS alone: 17 KiB per block instead of 87, three
+    // times the resident warps); slot[v] = position of series v among the wanted ones
+    int slot[5], nser = 0;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) slot[v] = a.out[v] ? nser++ : -1;
+    double *tile = sim_smem + 32 + (threadIdx.x >> 5) * (nser * 32 * SIM_LD);    // [nser][32][SIM_LD]
     if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     __syncthreads();
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;      // ncell_pad is a multiple of 32: whole warps leave together
@@ -621,12 +627,14 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
                     StepOut o = FAST ? step_fast(p, Pc_[u], Ec_[u], S, R, a.f32exp, tab)
                                      : step_literal(p, Pc_[u], Ec_[u], S, R, a.f32exp);
                     double *w = tile + lane * SIM_LD + (t - tb);
-                    w[0] = o.Pc;
-                    w[32 * SIM_LD] = o.AE;
-                    w[2 * 32 * SIM_LD] = S;
-                    w[3 * 32 * SIM_LD] = o.Q;
-                    const double qs = (p.area * o.Q) / Dc_[u];
-                    w[4 * 32 * SIM_LD] = a.round_qs ? r_round1(qs, fabs(qs) < 1e8 ? GR2M_TIE_THR : -1.0) : qs;
+                    if (slot[0] >= 0) w[slot[0] * 32 * SIM_LD] = o.Pc;
+                    if (slot[1] >= 0) w[slot[1] * 32 * SIM_LD] = o.AE;
+                    if (slot[2] >= 0) w[slot[2] * 32 * SIM_LD] = S;
+                    if (slot[3] >= 0) w[slot[3] * 32 * SIM_LD] = o.Q;
+                    if (slot[4] >= 0) {
+                        const double qs = (p.area * o.Q) / Dc_[u];
+                        w[slot[4] * 32 * SIM_LD] = a.round_qs ? r_round1(qs, fabs(qs) < 1e8 ? GR2M_TIE_THR : -1.0) : qs;
+                    }
                 }
             }
         }
@@ -638,7 +646,7 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_gr2m_sim(SimArgs a)
         for (int v = 0; v < 5; ++v) {
             double *__restrict__ dst = a.out[v];
             if (!dst) continue;
-            const double *src = tile + v * 32 * SIM_LD;
+            const double *src = tile + slot[v] * 32 * SIM_LD;
 #pragma unroll 4
             for (int r = sub; r < 32; r += 32 / SIM_MB) {
                 const int c = cell0 + r;
@@ -952,9 +960,9 @@ extern "C" int gr2m_run(gr2m_basin *b, const double *params, const double *S0, c
     a.ncell = b->ncell; a.ncell_pad = b->ncell_pad; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad;
     a.nreg = b->nreg; a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
     a.pitch = b->ntime; a.param_stride = 0; a.set_col = 0; a.round_qs = 0;
-    const size_t smem = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * sizeof(double);
+    const size_t smem = (32 + SIM_WARPS * (nout ? nout : 1) * 32 * SIM_LD) * sizeof(double);   // a tile per wanted series
     auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_MAX));
     CK(cudaEventRecord(b->ev0, b->stream));
     gr2m_count_launch(), kern<<<ceil_div(b->ncell_pad, SIM_WARPS * 32), SIM_WARPS * 32, smem, b->stream>>>(a);
     CK(cudaGetLastError());
@@ -1165,9 +1173,9 @@ extern "C" int gr2m_objective_routed_batch(gr2m_basin *b, wfa_router *r, const d
     DevBuf qs, qr;
     if ((rc = qs.ensure((size_t)chunk * per_set)) || (rc = qr.ensure((size_t)chunk * per_set))) { qs.release(); qr.release(); return rc; }
     const bool unr = (flags & GR2M_SINK_UNROUNDED) != 0;
-    const size_t smem = (32 + SIM_WARPS * 5 * 32 * SIM_LD) * sizeof(double);
+    const size_t smem = (32 + SIM_WARPS * 1 * 32 * SIM_LD) * sizeof(double);           // QS is the only series wanted
     auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_MAX);
     CK(cudaEventRecord(b->ev0, b->stream));
     for (int s0 = 0; s0 < nsets && e == cudaSuccess && !rc; s0 += chunk) {
         const int cs = std::min(chunk, nsets - s0);
