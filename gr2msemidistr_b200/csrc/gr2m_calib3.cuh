@@ -4,10 +4,13 @@
 // R/Run_GR2MSemiDistr.R:101-102), and with one region all lanes of a warp share X1, so both exponentials of a
 // month are exp(n c) with ONE c = 0.2/X1 per warp:  exp(n c) = exp(256 i c) * exp(j c),  n = 256 i + j.
 // Each warp builds T1h[i] = exp(min(256 i c, 26))/2 and T2[j] = exp(j c) (2 x 256 doubles, 4 KiB) once and a
-// month's exp becomes two shared-memory reads and one DMUL instead of 8 FP64-pipe instructions and a clamp
-// (airGR's min(WS, 13) is an integer min on n).  A tile where some lane could see n outside [0, 65535] (huge
-// forcing with a large X1, negative forcing or factors, unbounded input) or whose set has X1 < 1 (c > 0.2: the
-// clamped argument n_clamp c could overshoot 26 by more than 0.2) takes step_fast4, the general formulation.
+// month's exp becomes two shared-memory reads whose product enters the store updates through FMAs, instead of 8
+// FP64-pipe instructions and a clamp (airGR's min(WS, 13) is an integer min on n).  The rounding decision itself is
+// made in fixed point: ONE FMA per forcing value leaves n in the high word and the distance to the next decimal tie
+// in the low word of a double (step_tab_fx); a chunk in which any lane came within 2^-26 of a tie is repeated with
+// R's exact candidate comparison.  A tile where some lane could see n outside [0, 65535] (huge forcing with a large
+// X1, negative forcing or factors, unbounded input) or whose set has X1 < 1 (c > 0.2: the clamped argument n_clamp c
+// could overshoot 26 by more than 0.2) takes step_fast4, the general formulation.
 // Outlet sums go to global memory by fire-and-forget FP64 reductions (RED.ADD.F64): every (set, month) word is
 // only ever updated by one lane of one warp, in program order, so the sums are deterministic; this frees the
 // 30 KiB of per-CTA accumulators and lets the tables in.
