@@ -29,7 +29,7 @@ SYMBOLS = (
     "gr2m_objective_batch", "gr2m_objective_batch_dev", "gr2m_objective_routed_batch", "gr2m_basin_last_kernel_ms",
     "wfa_plan_create", "wfa_plan_create_dev", "wfa_plan_destroy", "wfa_plan_set_stream", "wfa_plan_info",
     "wfa_plan_export", "wfa_plan_basin_info", "wfa_plan_reach_info", "wfa_plan_segment_info", "wfa_router_create", "wfa_router_destroy",
-    "wfa_router_info", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
+    "wfa_router_info", "wfa_router_gauge_upstream", "wfa_router_apply", "wfa_router_apply_dev", "wfa_route", "wfa_accumulate", "wfa_accumulate_dev", "wfa_mask_dev",
     "wfa_plan_last_kernel_ms", "wfa_plan_last_phase_ms", "wfa_flowdir_from_dem", "wfa_flowdir_from_dem_dev",
 )
 
@@ -248,6 +248,14 @@ class Router:
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
         _check(lib().wfa_router_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(nnodes=a.value, nlevels=b.value, ncandidates=c.value, nactive=d.value)
+
+    def gauge_upstream(self, gauge: int):
+        """(nmax, owner[nsub]): the maximal candidate nodes of polygon `gauge` and, per subbasin, which of them it
+        drains through (-1: it does not reach the polygon)."""
+        n = C.c_int()
+        owner = np.empty(self.nsub, np.int32)
+        _check(lib().wfa_router_gauge_upstream(self._h, C.c_int(gauge), C.byref(n), _ip(owner)))
+        return n.value, owner
 
     def apply(self, QS):
         """QS [nsub, ncols] -> QR [nsub, ncols] (unrounded per-polygon maxima)."""

@@ -1139,6 +1139,87 @@ extern "C" int gr2m_objective_batch(gr2m_basin *b, const double *params, int nse
     return GR2M_OK;
 }
 
+// ---- routed objective at a gauge, fused (no QS / QR planes) ---------------------------------------------------------
+// For a fixed gauge polygon the routing is a linear functional of QS: QR_gauge = max over the polygon's maximal candidate
+// nodes of the sum of (rounded) QS over the node's upstream subbasins (wfa_router_gauge_owner, router.cu).  So the table-
+// mode recursion kernel computes it directly: one launch per maximal candidate with the areas of the other subbasins set
+// to zero and, unless GR2M_SINK_UNROUNDED, every subbasin's discharge rounded to 0.1 before the sum (k_gr2m_calib4<RQS>).
+__global__ void k_gauge_combine(const double *__restrict__ partial, int nk, int csplit, int nsets, int ntime, int round1,
+                                double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // set * ntime + month
+    if (i >= (long long)nsets * ntime) return;
+    double best = 0.0;
+    for (int k = 0; k < nk; ++k) {
+        const double *pk = partial + (size_t)k * csplit * nsets * ntime;
+        double s = 0.0;
+        for (int c = 0; c < csplit; ++c) s += pk[(size_t)c * nsets * ntime + i];
+        best = (k == 0 || s > best || isnan(s)) ? s : best;
+    }
+    out[i] = round1 ? r_round1(best, fabs(best) < 1e8 ? GR2M_TIE_THR : -1.0) : best;
+}
+
+// returns GR2M_OK with *done = 0 when the fused path does not apply (several regions, literal arithmetic, no or too many
+// maximal candidates): the caller then materialises QS and applies the operator
+static int routed_fused(gr2m_basin *b, wfa_router *r, int nsets, int gauge, int flags, double *series_dev, int *done)
+{
+    *done = 0;
+    const bool off = getenv("GR2M_ROUTED_MATERIALISE") != nullptr;      // cross-check switch, read at every call
+    if (off || b->nreg != 1 || (flags & GR2M_MATH_LITERAL) || getenv("GR2M_CALIB_GENERIC")) return GR2M_OK;
+    int rc, nk = 0;
+    std::vector<int32_t> owner(b->ncell);
+    if ((rc = wfa_router_gauge_owner(r, gauge, &nk, owner.data()))) return rc;
+    if (nk < 1 || nk > 4) return GR2M_OK;
+    const bool unr = (flags & GR2M_SINK_UNROUNDED) != 0;
+    int group_tiles = 4;
+    while (group_tiles * 64 < b->ntiles) group_tiles *= 2;
+    const int ngroups = ceil_div(b->ntiles, group_tiles), nsg = ceil_div(nsets, SPB);
+    int gps = (int)((long long)ngroups * nsg / ((long long)b->sm_count * 3 * 16));
+    if (gps < 1) gps = 1;
+    const size_t per_k = (size_t)ngroups * nsets * b->ntime;
+    DevBuf part, marea;
+    std::vector<double> area_h(b->ncell), masked((size_t)nk * b->ncell);
+    CK(cudaMemcpyAsync(area_h.data(), b->area.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < nk; ++k)
+        for (int c = 0; c < b->ncell; ++c) masked[(size_t)k * b->ncell + c] = owner[c] == k ? area_h[c] : 0.0;
+    if ((rc = part.ensure(nk * per_k * sizeof(double))) || (rc = marea.ensure(masked.size() * sizeof(double)))) {
+        part.release(); marea.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(marea.p, masked.data(), masked.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(part.p, 0, nk * per_k * sizeof(double), b->stream);
+    CalibArgs a;
+    a.F = b->F.as<double>(); a.params = b->params.as<double>(); a.tconv = b->conv.as<double>();
+    a.region = b->region.as<int>(); a.frange = b->frange.as<double>();
+    a.ncell = b->ncell; a.ntiles = b->ntiles; a.ntime = b->ntime; a.ntime_pad = b->ntime_pad; a.nreg = 1;
+    a.nsets = nsets; a.nsg = nsg; a.tiles_per_split = gps * group_tiles; a.group_tiles = group_tiles;
+    a.f32exp = (flags & GR2M_PERC_F32_EXPONENT) ? 1 : 0; a.forcing_ok = b->forcing_ok;
+    const size_t smem = (size_t)(RCB_DBL + CALIB4_NST * 2 * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * 2 * SPB * 32 + b->ntime_pad + 2) * sizeof(double) +
+                        CALIB4_NST * 12 + CALIB4_ALIGN_PAD;
+    void (*kern)(CalibArgs) = unr ? (a.f32exp ? k_gr2m_calib4<true, 3, 2, 3, false, true> : k_gr2m_calib4<false, 3, 2, 3, false, true>)
+                                  : (a.f32exp ? k_gr2m_calib4<true, 3, 2, 3, true, true> : k_gr2m_calib4<false, 3, 2, 3, true, true>);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nblk_split = ceil_div(b->ntiles, a.tiles_per_split);
+    for (int k = 0; k < nk && e == cudaSuccess; ++k) {
+        a.area = marea.as<double>() + (size_t)k * b->ncell;
+        a.partial = part.as<double>() + (size_t)k * per_k;
+        gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        const long long n = (long long)nsets * b->ntime;
+        gr2m_count_launch(), k_gauge_combine<<<ceil_div(n, 256), 256, 0, b->stream>>>(part.as<double>(), nk, ngroups, nsets, b->ntime,
+                                                                                 unr ? 0 : 1, series_dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    part.release(); marea.release();
+    if (e != cudaSuccess) { gr2m_set_error("gr2m_objective_routed_batch (fused): %s", cudaGetErrorString(e)); cudaGetLastError(); return GR2M_ERR_CUDA; }
+    *done = 1;
+    return GR2M_OK;
+}
+
 // Routed objective: the reference's Run -> Routing -> hydroGOF chain for many parameter sets at once.  Every set is
 // simulated for every subbasin (QS rounded to 0.1 like Run_GR2MSemiDistr returns it, Run:229-235), the sets x months
 // become the columns of ONE application of the month-invariant routing operator (wfa_router, Routing:100-123), the
@@ -1168,16 +1249,18 @@ extern "C" int gr2m_objective_routed_batch(gr2m_basin *b, wfa_router *r, const d
     if ((rc = b->partial.ensure((size_t)nsets * nt * sizeof(double)))) return rc;      // gauge series [set][month]
     CK(cudaMemcpyAsync(b->params.p, params, np * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     if ((rc = upload_qobs(b, qobs))) return rc;
+    CK(cudaEventRecord(b->ev0, b->stream));
+    int fused = 0;
+    if ((rc = routed_fused(b, r, nsets, gauge, flags, b->partial.as<double>(), &fused))) return rc;
     long long per_set = (long long)b->ncell * nt * 8;
     int chunk = (int)std::min<long long>(nsets, std::max<long long>(1, (1ll << 30) / per_set));
     DevBuf qs, qr;
-    if ((rc = qs.ensure((size_t)chunk * per_set)) || (rc = qr.ensure((size_t)chunk * per_set))) { qs.release(); qr.release(); return rc; }
+    if (!fused && ((rc = qs.ensure((size_t)chunk * per_set)) || (rc = qr.ensure((size_t)chunk * per_set)))) { qs.release(); qr.release(); return rc; }
     const bool unr = (flags & GR2M_SINK_UNROUNDED) != 0;
     const size_t smem = (32 + SIM_WARPS * 1 * 32 * SIM_LD) * sizeof(double);           // QS is the only series wanted
     auto kern = (flags & GR2M_MATH_LITERAL) ? k_gr2m_sim<false> : k_gr2m_sim<true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_MAX);
-    CK(cudaEventRecord(b->ev0, b->stream));
-    for (int s0 = 0; s0 < nsets && e == cudaSuccess && !rc; s0 += chunk) {
+    for (int s0 = 0; s0 < nsets && e == cudaSuccess && !rc && !fused; s0 += chunk) {
         const int cs = std::min(chunk, nsets - s0);
         SimArgs a;
         a.F = b->F.as<double>(); a.area = b->area.as<double>(); a.params = b->params.as<double>() + (size_t)s0 * 4 * b->nreg;

@@ -89,6 +89,18 @@ __device__ __forceinline__ double step_tab_core2(const CellPar &p, double np_, d
     return q;
 }
 
+// RQS: round(area Q / den, 1) decided by rint.  y = area X1 q (the caller's product), c10 = 10 / den[t]: x10 = 10 x up to
+// one rounding; away from a decimal tie (|x10 - rint(x10)| < GR2M_TIE_THR) and below 1e9 the result is the correctly
+// rounded n / 10 (div10_rn), which is what R's candidate comparison returns there; anything else (ties, huge values,
+// NaN) raises `tie` and the caller repeats the chunk through r_round1.
+__device__ __forceinline__ double round_qs_fast(double y, double c10, bool &tie)
+{
+    const double x10 = __dmul_rn(y, c10);
+    const double n = __dadd_rn(__dadd_rn(x10, KC.magic), KC.nmagic);
+    tie |= !(fabs(__dsub_rn(x10, n)) < KC.tie_thr) | !(x10 < 1e9);
+    return div10_rn(n);
+}
+
 // Table lookups of the fixed-point variant: `hi` is the high word of t = x + FX_C (below), whose bits 0..15 hold
 // n = floor(x + 1/2 + w); the tables sit at 2 KiB-aligned shared addresses, so an entry's address is two logic
 // instructions (shift, and-or) per level and n never has to exist as an integer of its own.
@@ -191,7 +203,13 @@ __device__ __forceinline__ double step_tab(const CellPar &p, const double *__res
 // ---------------------------------------------------------------------------------------------------------
 
 //  * MAGIC = 2 (shipped): rounding decision in fixed point (step_tab_fx); 0 / 1: the round-2 forms (step_tab_nb).
-template <bool F32EXP, int CTAS, int CPT, int MAGIC>
+//  * RQS (routed objective at a gauge, gr2m_objective_routed_batch): every subbasin's discharge area Q / den[t] is rounded
+//    to 0.1 with R's rule BEFORE it is summed (Run:229-235 rounds QS, Routing then accumulates the rounded values); the
+//    cells outside the gauge's upstream set come in with area 0.  The decision is rint(10 x) wherever 10 x is at
+//    least 1e-5 away from a decimal tie and below 1e9, anything else raises the chunk's redo flag and goes through
+//    r_round1 month by month.  conv10[t] = 10 / den[t] sits in shared memory.
+//  * MASKED (same caller): a tile pair whose 64 cells all carry area 0 is consumed without arithmetic.
+template <bool F32EXP, int CTAS, int CPT, int MAGIC, bool RQS = false, bool MASKED = false>
 __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
 {
     constexpr int NST = CALIB4_NST, STG = CPT * STAGE2_DBL;
@@ -205,6 +223,7 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
     double *saved = stage + NST * STG;                               // 2 * CPT * SPB * 32: stores at the start of a chunk
     uint64_t *full = reinterpret_cast<uint64_t *>(saved + 2 * CPT * SPB * 32);   // NST
     int *left = reinterpret_cast<int *>(full + NST);                 // NST: warps that have left the stage
+    double *conv10 = reinterpret_cast<double *>(left + NST + (NST & 1));         // RQS only: a.ntime_pad doubles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sg = blockIdx.x % a.nsg, cs = blockIdx.x / a.nsg;
@@ -222,6 +241,8 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
         mbar_fence_init();
     }
     for (int i = tid; i < RCB_DBL; i += SPB * 32) reinterpret_cast<float2 *>(rcb)[i] = g_rcbrt_lin[i];
+    if (RQS)
+        for (int i = tid; i < a.ntime_pad; i += SPB * 32) conv10[i] = i < a.ntime ? 10.0 * a.tconv[i] : 0.0;
     const uint32_t ctab = smem_u32(rcb);
     __syncthreads();
     // stage gi = 8 months (chunk gi % nchunk) of the CPT tiles of pair gi / nchunk: one 4 KiB bulk copy per tile
@@ -283,10 +304,16 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
         }
         const bool use_tab = __all_sync(0xffffffffu, lane_tab);
         const bool no_clamp = MAGIC == 3 && __all_sync(0xffffffffu, lane_noclamp);   // no month of the pair reaches nclamp
+        // a pair whose 64 cells all carry area 0 adds nothing to the sums (the routed objective masks the subbasins
+        // outside the gauge's upstream set this way): its stages are consumed without arithmetic
+        bool lane_live = !MASKED;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) lane_live = lane_live || !(aX1[c] == 0.0);
+        const bool pair_live = !MASKED || __any_sync(0xffffffffu, lane_live);
         for (int ch = 0; ch < nchunk; ++ch, ++g) {
             const int st = g % NST;
             mbar_wait(&full[st], (g / NST) & 1);
-            if (set_ok) {
+            if (set_ok && pair_live) {
                 const double *sp = stage + st * STG;
                 bool redo = true;
                 if (use_tab && !branchy) {
@@ -307,7 +334,12 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
                             for (int c = 0; c < CPT; ++c) {
                                 const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
                                 const double qc = step_tab_fx<F32EXP, false>(p, Pr, Er, S[c], R[c], t1, t2, ctab, hiclamp, tmin);
-                                v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                                if (RQS) {
+                                    const double qs = round_qs_fast(aX1[c] * qc, conv10[ch * TM2 + m], tie);
+                                    v[m] = c == 0 ? qs : v[m] + qs;
+                                } else {
+                                    v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                                }
                             }
                         }
                     } else {
@@ -318,16 +350,21 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
                                 const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
                                 const double qc = MAGIC >= 2 ? step_tab_fx<F32EXP, true>(p, Pr, Er, S[c], R[c], t1, t2, ctab, hiclamp, tmin)
                                                              : step_tab_nb<F32EXP, MAGIC>(p, Pr, Er, S[c], R[c], t1, t2, ctab, nclamp, tie);
-                                v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                                if (RQS) {
+                                    const double qs = round_qs_fast(aX1[c] * qc, conv10[ch * TM2 + m], tie);
+                                    v[m] = c == 0 ? qs : v[m] + qs;
+                                } else {
+                                    v[m] = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, v[m]);
+                                }
                             }
                         }
                     }
-                    if (MAGIC >= 2) tie = tmin < GR2M_FX_TIE;
+                    if (MAGIC >= 2) tie |= tmin < GR2M_FX_TIE;
                     redo = __any_sync(0xffffffffu, tie);
                     if (!redo) {
                         double s = warp_reduce8(v, lane);
                         const int t = ch * TM2 + ridx;
-                        if (writer && t < a.ntime) atomicAdd(myout + t, s * __ldg(a.tconv + t));
+                        if (writer && t < a.ntime) atomicAdd(myout + t, RQS ? s : s * __ldg(a.tconv + t));
                     } else {
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) {
@@ -350,11 +387,18 @@ __global__ void __launch_bounds__(SPB * 32, CTAS) k_gr2m_calib4(CalibArgs a)
                             const double Pr = sp[soff[c] + m * 64], Er = sp[soff[c] + m * 64 + 32];
                             const double qc = use_tab ? step_tab<F32EXP>(p, par, Pr, Er, S[c], R[c], t1, t2, ctab, nclamp)
                                                       : step_fast4<F32EXP>(p, Pr, Er, S[c], R[c], g_exp2_tab2048);
-                            q = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, q);
+                            if (RQS) {
+                                const int tt = ch * TM2 + m;
+                                const double x = __dmul_rn(aX1[c] * qc, tt < a.ntime ? __ldg(a.tconv + tt) : 0.0);
+                                const double qs = r_round1(x, fabs(x) < 1e8 ? GR2M_TIE_THR : -1.0);
+                                q = c == 0 ? qs : q + qs;
+                            } else {
+                                q = c == 0 ? aX1[0] * qc : __fma_rn(aX1[c], qc, q);
+                            }
                         }
                         q = warp_sum_f64(q);
                         const int t = ch * TM2 + m;
-                        if (lane == 0 && t < a.ntime) atomicAdd(myout + t, q * __ldg(a.tconv + t));
+                        if (lane == 0 && t < a.ntime) atomicAdd(myout + t, RQS ? q : q * __ldg(a.tconv + t));
                     }
                 }
             }

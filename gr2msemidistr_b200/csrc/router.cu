@@ -529,6 +529,64 @@ extern "C" int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_d
 // for gr2m_objective_routed_batch (gr2m.cu): number of subbasins, and "wait until the last apply is done"
 int wfa_router_nsub(const wfa_router *r) { return r ? r->nsub : -1; }
 int wfa_router_is_f32(const wfa_router *r) { return r && (r->flags & WFA_F32) ? 1 : 0; }
+// For gr2m_objective_routed_batch's fused path.  The routed discharge of one polygon is max over its candidate nodes of
+// the node's accumulated value = the sum of QS over the subbasins upstream of the node, so for a FIXED gauge the whole
+// routing collapses to weighted outlet sums.  In the node forest two nodes' upstream sets are nested or disjoint, and QS
+// is never negative, so only the candidates that do not descend from another candidate matter ("maximal" ones), and
+// their upstream sets are disjoint: owner[s] = index of the maximal candidate whose upstream set holds subbasin s, or -1.
+// Host-side walk over a copy of the forest (a few integers per node; done once per router and gauge by the caller).
+// *nmax = number of maximal candidates (0: the polygon has none -- the caller keeps the materialised path).
+int wfa_router_gauge_owner(wfa_router *r, int gauge, int *nmax, int32_t *owner_host)
+{
+    REQUIRE(r && nmax && owner_host, "NULL argument");
+    REQUIRE(gauge >= 0 && gauge < r->nsub, "gauge polygon index out of range");
+    CK(cudaSetDevice(r->device));
+    const int nn = r->nn;
+    for (int s = 0; s < r->nsub; ++s) owner_host[s] = -1;
+    *nmax = 0;
+    if (nn <= 0) return GR2M_OK;
+    std::vector<int32_t> nsrc(nn), coff(nn + 1), cidx(nn), goff(2);
+    CK(cudaStreamSynchronize(r->plan->stream));
+    CK(cudaMemcpy(nsrc.data(), r->node_src.p, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(coff.data(), r->child_off.p, ((size_t)nn + 1) * 4, cudaMemcpyDeviceToHost));
+    if (coff[nn] > 0) CK(cudaMemcpy(cidx.data(), r->child_idx.p, (size_t)coff[nn] * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(goff.data(), r->cand_off.as<int32_t>() + gauge, 8, cudaMemcpyDeviceToHost));
+    const int nc = goff[1] - goff[0];
+    if (nc <= 0) return GR2M_OK;
+    std::vector<int32_t> cand(nc);
+    CK(cudaMemcpy(cand.data(), r->cand_idx.as<int32_t>() + goff[0], (size_t)nc * 4, cudaMemcpyDeviceToHost));
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    std::vector<int32_t> parent(nn, -1);
+    for (int v = 0; v < nn; ++v)
+        for (int q = coff[v]; q < coff[v + 1]; ++q) parent[cidx[q]] = v;
+    std::vector<char> iscand(nn, 0);
+    for (int c : cand) iscand[c] = 1;
+    std::vector<int32_t> stack;
+    int k = 0;
+    for (int c : cand) {
+        bool maximal = true;
+        for (int v = parent[c]; v >= 0; v = parent[v])
+            if (iscand[v]) { maximal = false; break; }
+        if (!maximal) continue;
+        stack.assign(1, c);
+        while (!stack.empty()) {
+            const int v = stack.back();
+            stack.pop_back();
+            if (nsrc[v] >= 0) owner_host[nsrc[v]] = k;
+            for (int q = coff[v]; q < coff[v + 1]; ++q) stack.push_back(cidx[q]);
+        }
+        ++k;
+    }
+    *nmax = k;
+    return GR2M_OK;
+}
+
+extern "C" int wfa_router_gauge_upstream(wfa_router *r, int gauge, int *nmax, int32_t *owner)
+{
+    return wfa_router_gauge_owner(r, gauge, nmax, owner);
+}
+
 int wfa_router_wait(wfa_router *r)
 {
     REQUIRE(r != nullptr, "router is NULL");

@@ -131,6 +131,27 @@ def d8_grid(nrow: int, ncol: int, seed: int = SEED + 3, device="cpu", nodata_fra
     return code
 
 
+def d8_convergent(n: int, device="cpu"):
+    """A single convergent drainage tree on an n x n grid, by construction: cells above the main diagonal flow south,
+    cells below it flow east, the diagonal flows south-east and leaves through the south-east corner (outer ring
+    nodata; the row and column next to the north and west ring drain outwards, so the streams start on cells that
+    TauDEM's edge-contamination rule leaves clean).  With block_polygons every block centre drains through the last
+    block, whose interior the main stem crosses: one outlet polygon with the whole basin upstream, like a gauged
+    watershed."""
+    import torch
+    dev = torch.device(device)
+    rr = torch.arange(n, device=dev)[:, None]
+    cc = torch.arange(n, device=dev)[None, :]
+    code = torch.where(rr < cc, 7, torch.where(rr > cc, 1, 8)).to(torch.int16)
+    code[1, :] = 3
+    code[:, 1] = 5
+    code[0, :] = -32768
+    code[-1, :] = -32768
+    code[:, 0] = -32768
+    code[:, -1] = -32768
+    return code
+
+
 def fractal_dem(nrow: int, ncol: int, seed: int = SEED + 4, device="cpu", nodata_frac: float = 0.02, octaves: int = 5,
                 relief: float = 1.0):
     """SURVEY 8(d) terrain: plane tilted to the south-east + `octaves` octaves of value noise whose local slopes

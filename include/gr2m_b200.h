@@ -192,13 +192,23 @@ void wfa_router_destroy(wfa_router *r);
 int wfa_router_info(const wfa_router *r, int *nnodes, int *nlevels, int *ncandidates, long long *nactive);
 int wfa_router_apply(wfa_router *r, int ncols, const double *QS, double *QR);           /* host buffers */
 int wfa_router_apply_dev(wfa_router *r, int ncols, const double *QS_dev, double *QR_dev);
+/* Which subbasins feed polygon `gauge` (0-based): the routed discharge of a polygon is the maximum over its candidate
+ * nodes of the sum of QS over the node's upstream subbasins (Routing:119-123 on the operator's node forest).  With
+ * QS >= 0 only the candidates that do not descend from another candidate matter; their upstream sets are disjoint.
+ * *nmax = number of those; owner[s] (nsub entries) = index of the one whose set holds subbasin s, or -1 if s does
+ * not reach the polygon.  gr2m_objective_routed_batch uses it to skip the routing altogether (see there). */
+int wfa_router_gauge_upstream(wfa_router *r, int gauge, int *nmax, int32_t *owner);
 
 /* Routed objective (north_star's simulate + route + objective loop): the reference's chain Run_GR2MSemiDistr ->
  * Routing_GR2MSemiDistr -> hydroGOF for nsets parameter sets at once.  Per set: QS of every subbasin rounded to 0.1
  * (Run:229-235), routed by the operator (Routing:100-123; months x sets are its columns), QR of polygon `gauge`
  * (0-based) rounded to 0.1 (Routing:131), scored against qobs as in Optim:199-212.  GR2M_SINK_UNROUNDED skips both
  * roundings.  Outputs as gr2m_objective_batch (out_qt: the gauge series, [nsets][ntime]).  The router must be FP64 and
- * built for the basin's subbasins in the same order. */
+ * built for the basin's subbasins in the same order.
+ * With one region and at most four maximal candidates (wfa_router_gauge_upstream; a watershed polygon has one) nothing
+ * is materialised: the recursion kernel sums the rounded QS of the upstream subbasins directly, one launch per
+ * candidate, and subbasins that do not reach the gauge are not simulated.  Otherwise QS is written, the operator
+ * applied and the gauge row read back; environment GR2M_ROUTED_MATERIALISE=1 forces that path (cross-check). */
 int gr2m_objective_routed_batch(gr2m_basin *b, wfa_router *r, const double *params, int nsets, const double *qobs,
                                 int gauge, int warmup, int which, int flags, double *out_of, double *out_crit,
                                 double *out_qt); /* device, async */

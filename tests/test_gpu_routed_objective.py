@@ -99,3 +99,49 @@ def test_synthetic_many_sets_chunks_and_regions(capi, oracle, rng, monkeypatch):
     with pytest.raises(capi.GR2MError):
         with capi.Plan(d8) as plan, plan.router(src[:5], off[:6], cells[:off[5]]) as router, capi.Basin(P, E, area, nd, region, nreg) as b:
             b.objective_routed_batch(router, par, qobs, 0)         # router built for another set of subbasins
+
+
+def test_fused_gauge_path_matches_the_materialised_one(capi, oracle, rng, monkeypatch):
+    # one region: the routed objective runs fused (weighted, per-subbasin-rounded outlet sums of the gauge's maximal
+    # candidate nodes, no QS / QR planes).  Gauges with one and with several maximal candidates, rounded and unrounded,
+    # against the materialised path (GR2M_ROUTED_MATERIALISE=1) and the oracle chain.
+    nrow, ncol = 160, 192
+    d8 = synth.d8_grid(nrow, ncol, seed=15).numpy()
+    src, off, cells = synth.block_polygons(nrow, ncol, 8, 8, margin=1)
+    nsub, ntime = len(src), 48
+    P, E, area, nd = synth.forcing(nsub, ntime, seed=16)
+    region = np.zeros(nsub, np.int32)
+    par = synth.param_sets(21, seed=17)
+    with capi.Plan(d8) as plan, plan.router(src, off, cells) as router, capi.Basin(P, E, area, nd, region, 1) as b:
+        base = oracle.route(d8, oracle.run(P, E, area, nd, region, 1, par[0])["QS"], src, off, cells)
+        mean = np.where(np.isfinite(base), base, -1).mean(axis=1)
+        order = np.argsort(-mean)
+        qobs = synth.qobs_from(base[order[0]])
+        # the upstream sets behind the fused path: routing ones gives, at every polygon, the size of its largest set
+        ones = router.apply(np.ones((nsub, 1)))[:, 0]
+        for g in range(0, nsub, 5):
+            k, owner = router.gauge_upstream(g)
+            sizes = np.bincount(owner[owner >= 0], minlength=max(k, 1))
+            assert (k == 0 and not ones[g] > 0) or (k > 0 and sizes.max() == ones[g] and len(sizes) == k and sizes.min() > 0)
+        checked = fused = 0
+        # square blocks on a tilted plane are crossed by many parallel streams: a polygon with more than four maximal
+        # candidates keeps the materialised path, so try a spread of polygons and require that some ran fused
+        for gauge in [int(g) for g in order[::max(1, len(order) // 12)]]:
+            for fl in (0, capi.SINK_UNROUNDED):
+                n0 = capi.kernel_launches()
+                got = b.objective_routed_batch(router, par, qobs, gauge, 5, capi.OF_KGE, fl, want_qt=True)
+                fused += capi.kernel_launches() - n0 <= 6        # <= 4 recursion launches + combine + objective
+                monkeypatch.setenv("GR2M_ROUTED_MATERIALISE", "1")
+                mat = b.objective_routed_batch(router, par, qobs, gauge, 5, capi.OF_KGE, fl, want_qt=True)
+                monkeypatch.delenv("GR2M_ROUTED_MATERIALISE")
+                if fl:
+                    assert relerr(got["qt"], mat["qt"]) <= 1e-12
+                    want_qt, want_crit, _ = oracle_chain(oracle, P, E, area, nd, region, 1, par[:6], d8, src, off, cells, gauge, qobs, 5, False)
+                    assert relerr(got["qt"][:6], want_qt) <= TOL
+                    ok = np.isfinite(want_crit)
+                    assert relerr(got["crit"][:6][ok], want_crit[ok]) <= TOL
+                else:       # sums of values rounded to 0.1, rounded to 0.1: the same numbers unless a sum sits on a tie
+                    d = np.abs(got["qt"] - mat["qt"])
+                    assert np.all(d <= 0.1 + 1e-9) and np.mean(d > 1e-9) <= 1e-4
+                checked += 1
+        assert checked >= 16 and fused >= 4, (checked, fused)
