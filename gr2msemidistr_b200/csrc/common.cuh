@@ -37,6 +37,7 @@ int wfa_router_nsub(const wfa_router *r);      // router.cu
 int wfa_router_is_f32(const wfa_router *r);
 int wfa_router_wait(wfa_router *r);
 int wfa_router_gauge_owner(wfa_router *r, int gauge, int *nmax, int32_t *owner_host);   // see router.cu
+long long wfa_router_uid(const wfa_router *r);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -795,6 +795,9 @@ struct gr2m_basin {
     bool timed = false;
     int forcing_ok = 0;   // every |P|, |E| < 1e5 and finite (checked on the device at upload)
     DevBuf F, frange, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, s0, r0, send, rend;
+    DevBuf gauge_area;                  // routed objective, fused path: areas masked per maximal candidate of the last gauge
+    long long gauge_router = 0;         // ... keyed on (router uid, gauge polygon)
+    int gauge_poly = -1, gauge_nk = 0;
     double *qobs_host_copy = nullptr;   // last uploaded qobs (to skip re-uploads)
     int qobs_n = 0;
 };
@@ -805,7 +808,7 @@ static void basin_free(gr2m_basin *b)
     cudaSetDevice(b->device);
     FreeBatch fb;
     DevBuf *bufs[] = {&b->F, &b->frange, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
-                      &b->crit, &b->qobs, &b->sim_out, &b->s0, &b->r0, &b->send, &b->rend};
+                      &b->crit, &b->qobs, &b->sim_out, &b->s0, &b->r0, &b->send, &b->rend, &b->gauge_area};
     for (DevBuf *d : bufs) d->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -1167,8 +1170,24 @@ static int routed_fused(gr2m_basin *b, wfa_router *r, int nsets, int gauge, int 
     const bool off = getenv("GR2M_ROUTED_MATERIALISE") != nullptr;      // cross-check switch, read at every call
     if (off || b->nreg != 1 || (flags & GR2M_MATH_LITERAL) || getenv("GR2M_CALIB_GENERIC")) return GR2M_OK;
     int rc, nk = 0;
-    std::vector<int32_t> owner(b->ncell);
-    if ((rc = wfa_router_gauge_owner(r, gauge, &nk, owner.data()))) return rc;
+    if (b->gauge_router == wfa_router_uid(r) && b->gauge_poly == gauge) {
+        nk = b->gauge_nk;                                         // same router and gauge as the last call: masks are in place
+    } else {
+        std::vector<int32_t> owner(b->ncell);
+        if ((rc = wfa_router_gauge_owner(r, gauge, &nk, owner.data()))) return rc;
+        b->gauge_router = 0;
+        if (nk >= 1 && nk <= 4) {
+            std::vector<double> area_h(b->ncell), masked((size_t)nk * b->ncell);
+            CK(cudaMemcpyAsync(area_h.data(), b->area.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+            for (int k = 0; k < nk; ++k)
+                for (int c = 0; c < b->ncell; ++c) masked[(size_t)k * b->ncell + c] = owner[c] == k ? area_h[c] : 0.0;
+            if ((rc = b->gauge_area.ensure(masked.size() * sizeof(double)))) return rc;
+            CK(cudaMemcpyAsync(b->gauge_area.p, masked.data(), masked.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaStreamSynchronize(b->stream));                 // `masked` leaves scope
+        }
+        b->gauge_router = wfa_router_uid(r); b->gauge_poly = gauge; b->gauge_nk = nk;
+    }
     if (nk < 1 || nk > 4) return GR2M_OK;
     const bool unr = (flags & GR2M_SINK_UNROUNDED) != 0;
     int group_tiles = 4;
@@ -1177,18 +1196,9 @@ static int routed_fused(gr2m_basin *b, wfa_router *r, int nsets, int gauge, int 
     int gps = (int)((long long)ngroups * nsg / ((long long)b->sm_count * 3 * 16));
     if (gps < 1) gps = 1;
     const size_t per_k = (size_t)ngroups * nsets * b->ntime;
-    DevBuf part, marea;
-    std::vector<double> area_h(b->ncell), masked((size_t)nk * b->ncell);
-    CK(cudaMemcpyAsync(area_h.data(), b->area.p, b->ncell * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
-    for (int k = 0; k < nk; ++k)
-        for (int c = 0; c < b->ncell; ++c) masked[(size_t)k * b->ncell + c] = owner[c] == k ? area_h[c] : 0.0;
-    if ((rc = part.ensure(nk * per_k * sizeof(double))) || (rc = marea.ensure(masked.size() * sizeof(double)))) {
-        part.release(); marea.release();
-        return rc;
-    }
-    cudaError_t e = cudaMemcpyAsync(marea.p, masked.data(), masked.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(part.p, 0, nk * per_k * sizeof(double), b->stream);
+    DevBuf part;
+    if ((rc = part.ensure(nk * per_k * sizeof(double)))) { part.release(); return rc; }
+    cudaError_t e = cudaMemsetAsync(part.p, 0, nk * per_k * sizeof(double), b->stream);
     CalibArgs a;
     a.F = b->F.as<double>(); a.params = b->params.as<double>(); a.tconv = b->conv.as<double>();
     a.region = b->region.as<int>(); a.frange = b->frange.as<double>();
@@ -1202,7 +1212,7 @@ static int routed_fused(gr2m_basin *b, wfa_router *r, int nsets, int gauge, int 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int nblk_split = ceil_div(b->ntiles, a.tiles_per_split);
     for (int k = 0; k < nk && e == cudaSuccess; ++k) {
-        a.area = marea.as<double>() + (size_t)k * b->ncell;
+        a.area = b->gauge_area.as<double>() + (size_t)k * b->ncell;
         a.partial = part.as<double>() + (size_t)k * per_k;
         gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
         e = cudaGetLastError();
@@ -1214,7 +1224,7 @@ static int routed_fused(gr2m_basin *b, wfa_router *r, int nsets, int gauge, int 
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
-    part.release(); marea.release();
+    part.release();
     if (e != cudaSuccess) { gr2m_set_error("gr2m_objective_routed_batch (fused): %s", cudaGetErrorString(e)); cudaGetLastError(); return GR2M_ERR_CUDA; }
     *done = 1;
     return GR2M_OK;

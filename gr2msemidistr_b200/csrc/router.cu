@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -234,7 +235,10 @@ __global__ void k_rt_polymax(const int32_t *__restrict__ coff, const int32_t *__
 
 }  // namespace
 
+static std::atomic<long long> g_router_uid{0};
+
 struct wfa_router {
+    long long uid = ++g_router_uid;               // distinguishes routers that reuse an address (caches keyed on it)
     wfa_plan *plan = nullptr;
     int device = 0, nsub = 0, nn = 0, nh = 0, ncand = 0, flags = 0;
     long long nactive = 0;
@@ -581,6 +585,8 @@ int wfa_router_gauge_owner(wfa_router *r, int gauge, int *nmax, int32_t *owner_h
     *nmax = k;
     return GR2M_OK;
 }
+
+long long wfa_router_uid(const wfa_router *r) { return r ? r->uid : 0; }
 
 extern "C" int wfa_router_gauge_upstream(wfa_router *r, int gauge, int *nmax, int32_t *owner)
 {
