@@ -102,7 +102,7 @@ __device__ __forceinline__ double round_qs_fast(double y, double c10, bool &tie)
 }
 
 // Table lookups of the fixed-point variant: `hi` is the high word of t = x + FX_C (below), whose bits 0..15 hold
-// n = floor(x + 1/2 + w); the tables sit at 2 KiB-aligned shared addresses, so an entry's address is two logic
+// n = floor(x + 1/2 + w); each table level sits at a 2 KiB-aligned shared address, so an entry's address is two logic
 // instructions (shift, and-or) per level and n never has to exist as an integer of its own.
 __device__ __forceinline__ void pow_tab_ld(uint32_t hi, uint32_t t1, uint32_t t2, double &h, double &l)
 {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void pow_tab_ld(uint32_t hi, uint32_t t1, uint32_t t2
 
 // 1.5 * 2^20 + 1/2 + 2^-26: for 0 <= x < 65535, t = x + FX_C lies in [2^20, 2^21), where one ulp is 2^-32: the low
 // word of t is the fraction of x + 1/2 + 2^-26 in units of 2^-32 and the low 16 bits of the high word are its integer
-// part.  A low word below 2^7 (= 2 * 2^-26) means x is within 2^-26 = 1.5e-8 of a decimal tie (the DADD's own rounding,
+// part.  A low word below 2^7 (= 2 * 2^-26) means x is within 2^-26 = 1.5e-8 of a decimal tie (the FMA's own rounding,
 // 2^-33, cannot hide one: a sum rounded up to the next integer has a zero low word); everywhere else
 // floor(x + 1/2 + 2^-26) = rint(x) = the integer R's round(f x, 1) settles on (ulp(x) <= 1.5e-11 here).
 #define GR2M_FX_C 1572864.500000014901161193847656250
