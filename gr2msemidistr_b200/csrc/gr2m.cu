@@ -795,6 +795,8 @@ struct gr2m_basin {
     bool timed = false;
     int forcing_ok = 0;   // every |P|, |E| < 1e5 and finite (checked on the device at upload)
     DevBuf F, frange, area, region, den, conv, params, partial, qt, of, crit, qobs, sim_out, s0, r0, send, rend;
+    DevBuf region_area, region_params;  // several regions, cells mostly grouped by region: areas masked per region [nreg][ncell]
+                                        // (table-mode recursion, one pass per region) and the per-region parameters of a batch
     DevBuf gauge_area;                  // routed objective, fused path: areas masked per maximal candidate of the last gauge
     long long gauge_router = 0;         // ... keyed on (router uid, gauge polygon)
     int gauge_poly = -1, gauge_nk = 0;
@@ -808,7 +810,8 @@ static void basin_free(gr2m_basin *b)
     cudaSetDevice(b->device);
     FreeBatch fb;
     DevBuf *bufs[] = {&b->F, &b->frange, &b->area, &b->region, &b->den, &b->conv, &b->params, &b->partial, &b->qt, &b->of,
-                      &b->crit, &b->qobs, &b->sim_out, &b->s0, &b->r0, &b->send, &b->rend, &b->gauge_area};
+                      &b->crit, &b->qobs, &b->sim_out, &b->s0, &b->r0, &b->send, &b->rend, &b->gauge_area, &b->region_area,
+                      &b->region_params};
     for (DevBuf *d : bufs) d->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -866,6 +869,25 @@ static int basin_create_common(int ntime, int ncell, const double *P, const doub
     }
     step(cudaMemcpyAsync(b->area.p, area, ncell * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     step(cudaMemcpyAsync(b->region.p, region_id, ncell * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    // Several regions: the table-mode recursion needs one X1 per warp, i.e. one region per pair of cell tiles (64
+    // consecutive subbasins).  It is run once per region with the other regions' areas set to zero (pairs without a
+    // cell of the region are skipped, k_gr2m_calib4<MASKED>) -- worth it when the subbasins are mostly grouped by region,
+    // so that the passes together touch little more than every pair once; otherwise the general kernel serves.
+    std::vector<double> rarea;
+    if (nreg > 1 && nreg <= 64 && e == cudaSuccess) {
+        const int npairs = ceil_div(b->ntiles, 2);
+        long long touched = 0;
+        std::vector<unsigned long long> seen(npairs, 0ull);
+        for (int c = 0; c < ncell; ++c) seen[c >> 6] |= 1ull << region_id[c];
+        for (int p = 0; p < npairs; ++p) touched += __builtin_popcountll(seen[p]);
+        if (touched * 4 <= (long long)npairs * 5 + 4 * nreg) {
+            rarea.assign((size_t)nreg * ncell, 0.0);
+            for (int c = 0; c < ncell; ++c) rarea[(size_t)region_id[c] * ncell + c] = area[c];
+            int rr = b->region_area.ensure(rarea.size() * sizeof(double));
+            if (rr) { free(den); rawP.release(); rawE.release(); basin_free(b); return rr; }
+            step(cudaMemcpyAsync(b->region_area.p, rarea.data(), rarea.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        }
+    }
     step(cudaMemcpyAsync(b->den.p, den, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     step(cudaMemcpyAsync(b->conv.p, den + ntime, ntime * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     if (e == cudaSuccess) {
@@ -1011,6 +1033,15 @@ static int upload_qobs(gr2m_basin *b, const double *qobs)
     return GR2M_OK;
 }
 
+// params [nsets][X1 x nreg | X2 x nreg | Fpp x nreg | Fpe x nreg] (Run:85-88) -> out [nreg][nsets][X1, X2, Fpp, Fpe]
+__global__ void k_region_params(const double *__restrict__ params, int nsets, int nreg, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nreg * nsets * 4) return;
+    const int j = (int)(i & 3), set = (int)((i >> 2) % nsets), r = (int)((i >> 2) / nsets);
+    out[i] = params[(size_t)set * 4 * nreg + (size_t)j * nreg + r];
+}
+
 static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, const double *qobs, int warmup,
                             int which, int flags, double *of_dev, double *crit_dev, double *qt_dev)
 {
@@ -1021,7 +1052,8 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
     const bool fast = !(flags & GR2M_MATH_LITERAL);
     // one region: per-set power tables (gr2m_calib3.cuh); several regions: a lane's X1 depends on its cell
     static const bool no_tab = getenv("GR2M_CALIB_GENERIC") != nullptr;
-    const bool tabmode = fast && b->nreg == 1 && !no_tab;
+    const bool tabmulti = fast && b->nreg > 1 && !no_tab && b->region_area.p != nullptr;     // one table-mode pass per region
+    const bool tabmode = fast && !no_tab && (b->nreg == 1 || tabmulti);
     const int nsg = ceil_div(nsets, SPB);
     int csplit, tiles_per_split, group_tiles = 0;
     if (tabmode) {
@@ -1061,7 +1093,7 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         static const int ctas = getenv("GR2M_CALIB_CTAS") ? atoi(getenv("GR2M_CALIB_CTAS")) : 3;   // experiment switches
         static const int cpt = getenv("GR2M_CALIB_CPT") ? atoi(getenv("GR2M_CALIB_CPT")) : 2;
         static const int magic = getenv("GR2M_CALIB_MAGIC") ? atoi(getenv("GR2M_CALIB_MAGIC")) : 3;
-        const int c = cpt == 1 ? 1 : cpt == 4 ? 4 : 2;
+        const int c = tabmulti ? 2 : cpt == 1 ? 1 : cpt == 4 ? 4 : 2;
         const size_t smem = (size_t)(RCB_DBL + CALIB4_NST * c * STAGE2_DBL + SPB * PT_WARP_DBL + 2 * c * SPB * 32) * sizeof(double) +
                             CALIB4_NST * 12 + CALIB4_ALIGN_PAD;
         void (*kern)(CalibArgs) = k_gr2m_calib4<false, 3, 2, 2>;
@@ -1073,10 +1105,26 @@ static int launch_objective(gr2m_basin *b, const double *params_dev, int nsets, 
         else if (magic == 1) kern = k_gr2m_calib4<false, 3, 2, 1>;
         else if (magic == 0) kern = k_gr2m_calib4<false, 3, 2, 0>;
         const int nblk_split = ceil_div(b->ntiles, tiles_per_split);
+        if (tabmulti) {
+            kern = a.f32exp ? k_gr2m_calib4<true, 3, 2, 3, false, true> : k_gr2m_calib4<false, 3, 2, 3, false, true>;
+            if ((rc = b->region_params.ensure((size_t)b->nreg * nsets * 4 * sizeof(double)))) return rc;
+        }
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, b->stream));
         CK(cudaMemsetAsync(b->partial.p, 0, (size_t)csplit * nsets * b->ntime * sizeof(double), b->stream));
-        gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
+        if (tabmulti) {
+            const long long np4 = (long long)b->nreg * nsets * 4;
+            gr2m_count_launch(), k_region_params<<<ceil_div(np4, 256), 256, 0, b->stream>>>(params_dev, nsets, b->nreg,
+                                                                                       b->region_params.as<double>());
+            a.nreg = 1;
+            for (int r = 0; r < b->nreg; ++r) {       // passes add into the same partial words one after another: deterministic
+                a.params = b->region_params.as<double>() + (size_t)r * nsets * 4;
+                a.area = b->region_area.as<double>() + (size_t)r * b->ncell;
+                gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
+            }
+        } else {
+            gr2m_count_launch(), kern<<<nsg * nblk_split, SPB * 32, smem, b->stream>>>(a);
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, b->stream));
     } else {

@@ -324,3 +324,33 @@ def test_sums_do_not_depend_on_batch_size_or_rank_count(capi, nreg):
         for lo, hi in ((0, 1), (5, 13), (100, 260), (633, 640)):
             part = b.objective_batch(par[lo:hi], None, 0, capi.OF_NSE, capi.SINK_UNROUNDED, want_crit=False, want_qt=True)["qt"]
             assert np.array_equal(part, full[lo:hi]), (lo, hi)
+
+
+def test_regions_grouped_by_subbasin_take_the_table_mode_passes(capi, oracle, rng):
+    # several regions whose subbasins are (mostly) consecutive: the table-mode recursion runs once per region with the
+    # other regions' areas masked (tile pairs without a cell of the region are skipped); interleaved regions keep the
+    # general kernel.  Same parity bar, sums independent of the batch, and the launch count tells which path ran.
+    ncell, ntime, nreg = 1500, 60, 3
+    P, E, area, nd = synth.forcing(ncell, ntime, seed=81)
+    P[7] = 0.0; P[700, ::2] = 25.0; P[1400] = 2500.0
+    region = np.repeat(np.arange(nreg), [517, 420, 563]).astype(np.int32)        # ragged boundaries inside tile pairs
+    region[[3, 900, 1499]] = [2, 0, 1]                                            # a few strays
+    par = synth.param_sets(45, nreg, seed=82)
+    par[1, :nreg] = [1.0, 2000.0, 30.0]                                           # clamp in one region only
+    base = oracle.run(P, E, area, nd, region, nreg, par[0])
+    qobs = synth.qobs_from(oracle.outlet_optim(base["QS"]))
+    for fl in (0, capi.PERC_F32_EXPONENT):
+        with capi.Basin(P, E, area, nd, region, nreg) as b:
+            n0 = capi.kernel_launches()
+            got = b.objective_batch(par, qobs, 12, capi.OF_NSE, fl | capi.SINK_UNROUNDED, want_qt=True)
+            assert capi.kernel_launches() - n0 == nreg + 2       # parameter gather + one recursion pass per region + objective
+            one = b.objective_batch(par[9:10], qobs, 12, capi.OF_NSE, fl | capi.SINK_UNROUNDED, want_qt=True)
+        ref = oracle.objective_batch(P, E, area, nd, region, nreg, par, qobs, 12, flags=(fl & 1) | oracle.SINK_UNROUNDED, nthreads=4)
+        assert relerr(got["qt"], ref["qt"]) <= TOL
+        ok = np.isfinite(ref["crit"])
+        assert np.array_equal(np.isfinite(got["crit"]), ok) and relerr(got["crit"][ok], ref["crit"][ok]) <= TOL
+        assert np.array_equal(one["qt"][0], got["qt"][9])
+    with capi.Basin(P, E, area, nd, (np.arange(ncell) % nreg).astype(np.int32), nreg) as b:      # interleaved: general kernel
+        n0 = capi.kernel_launches()
+        b.objective_batch(par, qobs, 12, capi.OF_NSE, capi.SINK_UNROUNDED)
+        assert capi.kernel_launches() - n0 == 2
