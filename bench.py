@@ -350,9 +350,11 @@ def bench_routing(a, capi, torch, rank, world, dist, terrain="tilted"):
     if os.path.exists(peaks_file):
         hbm, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     gbs = units / world * 16.0 / (ms * 1e-3) / 1e9
-    # DRAM bytes per 32-month pass from the ncu launch list of the same grid (profiles/r1_wide_levels_traffic.txt): the wide
-    # levels move 190.4 GB = 14.9 B per grid cell and month; scaled to this pass's cells x months
-    traffic = 190.4e9 / (4.0e8 * 32) * float(ncell) * my_months if (n == 20000 and terrain == "tilted") else None
+    # DRAM bytes of one 32-month sweep of the 20000^2 grid, summed over its launches (ncu, profiles/r2_route_traffic.txt):
+    # 202.7 GB on the tilted grid, 239.2 GB on the filled one, against 204.8 GB algorithmic; scaled to this rank's months
+    per_sweep = {"tilted": 202.7e9, "filled": 239.2e9}[terrain]
+    traffic = per_sweep * my_months / 32.0 if n == 20000 else None
+    real_gbs = traffic / (ms * 1e-3) / 1e9 if traffic else None
     out = {"metric": "routed_cell_months_per_sec", "value": units / (ms * 1e-3), "unit": UNIT,
            "workload": f"C5 WFA: {n} x {n} synthetic D8 grid x {months_total} months, dense FP64 weights, "
                        f"{ld}-month batches, months sharded over {world} GPU(s)",
@@ -367,14 +369,15 @@ def bench_routing(a, capi, torch, rank, world, dist, terrain="tilted"):
                                          "by every sweep; this figure charges it to this one pass over the months",
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "traffic": traffic, "algorithmic_bytes_per_unit": 16, "peak_source": hbm_src,
-                        "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum summed over the level launches of this "
-                                       "rank's months (ncu, levels 1-120 = 96 % of the non-source cells), not per launch: a "
-                                       "sweep is ~600 launches of one kernel",
-                        "traffic_note": "ncu dram__bytes per launch, one 32-month sweep of the 20000^2 grid: levels 1-120 (212 M of the "
-                                        "220 M non-source cells) move 140.0 GB read + 50.4 GB written in 36.6 ms = 5.2 TB/s, "
-                                        "against 204.8 GB algorithmic for the whole sweep (source cells, 45 %, cost no traffic; "
-                                        "every other cell reads its row and 1.2-1.8 upstream rows and writes its row) "
-                                        "(profiles/r1_wide_levels_traffic.txt, r1_route_ncu_full.txt)"}}
+                        "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of this rank's "
+                                       "sweeps (a 32-month sweep is 250-600 launches: chain-segment levels + reach gather + "
+                                       "reach sweep), ncu on one sweep of the same grid scaled by months "
+                                       "(profiles/r2_route_traffic.txt)",
+                        "achieved_real_bytes": real_gbs, "frac_real_bytes": real_gbs / hbm if real_gbs else None,
+                        "traffic_note": "tilted grid: 202.7 GB moved per sweep = the algorithmic 204.8 GB (source cells cost "
+                                        "8 B, the chain segments keep the re-read of a predecessor row out of DRAM); filled grid "
+                                        "(few sources, sheet flow): 239.2 GB = 1.17 x algorithmic, i.e. the sweep runs at "
+                                        "frac_real_bytes of the copy bandwidth in bytes actually moved"}}
     out["basins"] = plan.basin_info()
     out["reaches"] = plan.reach_info()
     del A

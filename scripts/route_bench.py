@@ -10,6 +10,7 @@ ap.add_argument("--n", type=int, default=8000)
 ap.add_argument("--batches", default="16,32")
 ap.add_argument("--flags", default="0,128")
 ap.add_argument("--terrain", default="tilted", choices=["tilted", "filled"])
+ap.add_argument("--reps", type=int, default=3, help="sweeps per variant (1 under ncu)")
 a = ap.parse_args()
 g.build(); capi.set_device(0)
 dev = torch.device("cuda", 0)
@@ -35,7 +36,7 @@ for ld in [int(x) for x in a.batches.split(",")]:
     A = torch.empty((a.n * a.n, ld), dtype=torch.float64, device=dev)
     for fl in [int(x) for x in a.flags.split(",")]:
         best = 1e30
-        for rep in range(3):
+        for rep in range(a.reps):
             torch.manual_seed(1); A.uniform_(0.0, 100.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); plan.accumulate_dev(A.data_ptr(), ld, ld, fl); e1.record(); e1.synchronize()
